@@ -1,0 +1,186 @@
+"""Generate tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE from /root/reference (authoring container only).
+
+TEST INFRASTRUCTURE ONLY. Usage:  python -m oracle.gen_golden            (from the repo root)
+
+The reference cannot travel to the GPU box, so its outputs on seeded synthetic inputs are committed as small fixtures:
+
+  geometry_g{9,13,19}.npz  StonesFinder.getrect / getmask / zone_area / PosGrid.mtx   (stonesfinder.py:412-493,964-981)
+                           one process per board size: gsize is an import-time constant of the reference
+  clustering_stream.npz    SfClustering driven through StonesFinder._doframe for 7 frames of a 320x240 clip:
+                           goban_img, accu, piped bulk moves (stonesfinder.py:123-152, sf_clustering.py:23-46)
+  clustering_full.npz      SfClustering.find_stones / cluster_colors on whole-board uint8 images (sf_clustering.py:48-129)
+  neural_geometry.npz      NNManager geometry + codec + class_indices (nn_manager.py:92-126,216-275,360-382) and the
+                           reference's own known-answer tests (test/camkifu/stone/test_tmanager.py:18-27)
+  neural_decode.npz        NNCache.predict_all_stones + SfNeural.predict_all with a scripted net (nn_cache.py:25-52,
+                           sf_neural.py:57-70)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+CODE = {'E': 0, 'B': 1, 'W': 2}
+
+
+def codes(obj_arr):
+    return np.vectorize(CODE.get)(obj_arr).astype(np.uint8)
+
+
+def gen_geometry():
+    from oracle import refimport
+    refimport.load()
+    from golib.config.golib_conf import gsize
+    from camkifu.stone.stonesfinder import StonesFinder
+    sf = StonesFinder(refimport.FakeVManager(None, gsize), learn_bg=False)
+    rects = np.array([[sf.getrect(r, c) for c in range(gsize)] for r in range(gsize)], dtype=np.int32)
+    mask = sf.getmask().astype(np.uint8)
+    # pixels outside every zone are np.empty garbage in the reference (stonesfinder.py:468): blank them for comparison
+    cover = np.zeros_like(mask)
+    for r in range(gsize):
+        for c in range(gsize):
+            x0, y0, x1, y1 = rects[r, c]
+            cover[x0:x1, y0:y1] = 1
+    mask *= cover
+    np.savez_compressed(os.path.join(GOLD, "geometry_g%d.npz" % gsize), rects=rects, mask=mask, cover=cover,
+                        zone_area=np.int64(sf.zone_area), posgrid=sf._posgrid.mtx,
+                        canonical_size=np.int64(sf.canonical_shape[0]))
+    print("geometry", gsize, "zone_area", sf.zone_area)
+
+
+def gen_clustering():
+    import cv2
+    from oracle import refimport
+    from camkifu_b200 import synth
+    refimport.load()
+    from camkifu.stone.sf_clustering import SfClustering
+
+    # --- streaming: the real _doframe -> _find path, 7 frames (find_stones fires at frames 0, 3, 6)
+    frames, mtx, truth, corners = synth.make_clip(11, 7, 240, 320, new_board_every=3)
+    vm = refimport.FakeVManager(mtx)
+    sf = SfClustering(vm)
+    del sf.bg_model  # learn_bg has no effect on the outputs recorded here (MOG2 only feeds get_foreground())
+    gobans, accus, moves, seeds = [], [], [], []
+    for i in range(frames.shape[0]):
+        seed = 1000 + i
+        cv2.setRNGSeed(seed)
+        n0 = len(vm.controller.piped)
+        sf._doframe(frames[i].copy())
+        sf.total_f_processed += 1  # what VidProcessor.execute does after _doframe (video.py:106-107)
+        gobans.append(sf.goban_img.copy())
+        accus.append(sf.accu.copy())
+        bulk = [a for (ins, a) in vm.controller.piped[n0:] if ins == "bulk"]
+        mv = np.array([(CODE[m.color], m.y, m.x) for m in bulk[0][0]], dtype=np.int32) if bulk else np.zeros((0, 3), np.int32)
+        moves.append(mv)
+        seeds.append(seed)
+    np.savez_compressed(os.path.join(GOLD, "clustering_stream.npz"), frames=frames, mtx=mtx, truth=truth,
+                        goban=np.array(gobans), accu_last=accus[-1], accu_1=accus[1], seeds=np.array(seeds),
+                        board=codes(vm.controller.stones),
+                        **{"moves_%d" % i: m for i, m in enumerate(moves)})
+    print("stream: board matches truth at", (codes(vm.controller.stones)[:, 6:13] == truth[-1][:, 6:13]).mean())
+
+    # --- whole-board find_stones on uint8 canonical images
+    out = {}
+    for k, seed in enumerate((21, 22, 23)):
+        fr, M, tr, _ = synth.make_clip(seed, 1, 240, 320)
+        g = cv2.warpPerspective(fr[0], M, (380, 380))
+        cv2.setRNGSeed(seed)
+        ratios, centers = sf.cluster_colors(g.astype(np.float32))
+        cv2.setRNGSeed(seed)
+        stones = sf.find_stones(g)
+        out["goban_%d" % k] = g
+        out["ratios_%d" % k] = ratios
+        out["centers_%d" % k] = centers
+        out["stones_%d" % k] = codes(stones) if stones is not None else np.full((19, 19), 255, np.uint8)
+        out["truth_%d" % k] = tr[0]
+    # a low-density board: find_stones must return None (check_density, sf_clustering.py:170-178)
+    rng = np.random.default_rng(5)
+    st = np.zeros((19, 19), np.uint8)
+    st[3, 3] = 1
+    corners = synth.random_corners(rng, 240, 320)
+    M = synth.board_homography(corners, 380)
+    g = cv2.warpPerspective(synth.render_frame(rng, 240, 320, st, corners), M, (380, 380))
+    cv2.setRNGSeed(77)
+    res = sf.find_stones(g)
+    out["goban_sparse"] = g
+    out["sparse_is_none"] = np.bool_(res is None)
+    # a sub-region call as SfMeta makes them (sf_meta.py:253)
+    cv2.setRNGSeed(31)
+    res = sf.find_stones(out["goban_0"], rs=6, re=13, cs=12, ce=19)
+    out["stones_region"] = codes(res) if res is not None else np.full((19, 19), 255, np.uint8)
+    out["seeds"] = np.array([21, 22, 23, 77, 31])
+    np.savez_compressed(os.path.join(GOLD, "clustering_full.npz"), **out)
+    print("full-board: accuracy", [(out["stones_%d" % k] == out["truth_%d" % k]).mean() for k in range(3)],
+          "sparse none:", out["sparse_is_none"])
+
+
+def gen_neural():
+    import cv2
+    from oracle import refimport
+    from oracle import oracle as O
+    from camkifu_b200 import synth, weights
+    refimport.load()
+    from camkifu.stone.nn_manager import NNManager
+    from camkifu.stone.nn_cache import NNCache
+    import camkifu.stone.sf_neural as sfn
+
+    m = NNManager()
+    origins = np.array([[m._get_rect_nn(*m._subregion(i, j)) for j in range(10)] for i in range(10)], np.int32)
+    subregions = np.array([[m._subregion(i, j) for j in range(10)] for i in range(10)], np.int32)
+    stones_of_label = np.array([codes(NNManager.compute_stones(k)) for k in range(81)], np.uint8)
+    kat = {27: "EEEB", 36: "EEBB", 64: "BEBW"}  # test_tmanager.py:19-21
+    for k, s in kat.items():
+        assert "".join(NNManager.compute_stones(k)) == s
+    ci = m.class_indices()
+    assert list(ci[3, 2]) == list(range(54, 81)) and list(ci[0, 2]) == list(range(2, 81, 3))  # test_tmanager.py:23-27
+    allB = np.full((2, 2), 'B', dtype=object)
+    fr, M, tr, _ = synth.make_clip(41, 1, 240, 320)
+    g = cv2.warpPerspective(fr[0], M, (380, 380))
+    xs = m.generate_xs(g)
+    np.savez_compressed(os.path.join(GOLD, "neural_geometry.npz"), rect_nn=origins, subregions=subregions,
+                        stones_of_label=stones_of_label, class_indices=ci, label_allB=np.int64(
+                            NNManager.compute_label(0, 2, 0, 2, allB)), goban=g, xs=xs,
+                        split=np.int64(m.split), step=np.int64(m.step), nb_classes=np.int64(m.nb_classes),
+                        r_width=np.int64(m.r_width), c_width=np.int64(m.c_width))
+
+    # decode path with a scripted net: y comes from the C oracle's forward on seeded Glorot weights
+    params = weights.glorot_params(seed=0)
+    y = O.c_cnn_forward(xs, params)
+
+    class ScriptedNet:
+        def __init__(self):
+            self.k = 0
+
+        def predict(self, x):
+            assert x.shape == (1, 40, 40, 3)
+            idx = [i for i in range(100) if np.array_equal(xs[i], x[0])][0]
+            return y[idx][None]
+
+    NNManager._network = ScriptedNet()
+    cache = NNCache(m, g)
+    st = cache.predict_all_stones()
+    vm = refimport.FakeVManager(M)
+    sf = sfn.SfNeural(vm)
+    sf.cache = NNCache(sf.manager, g)
+    sf.predict_all()
+    bulk = [a for (ins, a) in vm.controller.piped if ins == "bulk"]
+    mv = np.array([(CODE[q.color], q.y, q.x) for q in bulk[0][0]], dtype=np.int32) if bulk else np.zeros((0, 3), np.int32)
+    np.savez_compressed(os.path.join(GOLD, "neural_decode.npz"), y=y, stones=codes(st[:, :, 0]),
+                        conf=st[:, :, 1].astype(np.float32), moves=mv, min_confidence=np.float64(sfn.MIN_CONFIDENCE))
+    print("neural: kept", len(mv), "moves; conf range", float(st[:, :, 1].min()), float(st[:, :, 1].max()))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "geometry":
+        gen_geometry()
+    elif what == "all":
+        for g in (9, 13, 19):
+            subprocess.run([sys.executable, "-m", "oracle.gen_golden", "geometry"], check=True, cwd=ROOT,
+                           env=dict(os.environ, CKB_GSIZE=str(g)))
+        gen_clustering()
+        gen_neural()
