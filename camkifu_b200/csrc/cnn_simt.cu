@@ -1,0 +1,218 @@
+// K4, verification variant — the SfNeural forward pass on plain fp32 CUDA cores (FMA), plus the softmax / decode
+// kernels shared with the tensor-core path.
+//
+// Replaces NNCache.predict_all_stones (src/camkifu/stone/nn_cache.py:25-52): 100 x (NNManager._get_x + net.predict) and
+// the base-3 decode of NNManager.compute_stones (nn_manager.py:246-254) with confidence max(y)/sum(y), and the
+// MIN_CONFIDENCE = 0.6 rule of SfNeural.predict_all (sf_neural.py:18,57-70).
+//
+// This direct-convolution path exists so that every tensor-core layer can be checked on the device against an
+// independent fp32 implementation (tests/test_gpu_cnn.py); ckb_cnn_forward (cnn_tc.cu) is the product path.
+#include "cnn_common.cuh"
+
+// out[p][oy][ox][co] = relu(b[co] + sum_{dy,dx,c} in[p][oy+dy][ox+dx][c] * w[dy][dx][c][co]); thread <-> (p, oy, ox, co)
+// U8IN: the input is the canonical image itself and patch p = (frame, i, j) is read in place (NNManager._get_x).
+template <int KH, int KW, int CIN, int COUT, int IH, int IW, bool U8IN>
+__global__ void __launch_bounds__(256) cnn_conv_relu_simt(const void *__restrict__ in, const float *__restrict__ w,
+                                                          const float *__restrict__ b, float *__restrict__ out,
+                                                          int n_patches)
+{
+    constexpr int OH = IH - KH + 1, OW = IW - KW + 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_patches * OH * OW * COUT;
+    if (idx >= total) return;
+    const int co = (int)(idx % COUT);
+    long long t = idx / COUT;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int p = (int)(t / OH);
+    float acc = 0.f;
+    if (U8IN) {
+        const int frame = p / 100, r = p % 100;
+        const int x0 = cnn_patch_origin(r / 10), y0 = cnn_patch_origin(r % 10);
+        const uint8_t *img = (const uint8_t *)in + (size_t)frame * 380 * 380 * 3;
+        for (int dy = 0; dy < KH; dy++)
+            for (int dx = 0; dx < KW; dx++) {
+                const uint8_t *ip = img + ((size_t)(x0 + oy + dy) * 380 + (y0 + ox + dx)) * 3;
+                const float *wp = w + (size_t)((dy * KW + dx) * CIN) * COUT + co;
+#pragma unroll
+                for (int c = 0; c < CIN; c++) acc = fmaf((float)__ldg(ip + c), __ldg(wp + c * COUT), acc);
+            }
+    } else {
+        const float *base = (const float *)in + (size_t)p * IH * IW * CIN;
+        for (int dy = 0; dy < KH; dy++)
+            for (int dx = 0; dx < KW; dx++) {
+                const float *ip = base + ((size_t)(oy + dy) * IW + (ox + dx)) * CIN;
+                const float *wp = w + (size_t)((dy * KW + dx) * CIN) * COUT + co;
+#pragma unroll 8
+                for (int c = 0; c < CIN; c++) acc = fmaf(__ldg(ip + c), __ldg(wp + c * COUT), acc);
+            }
+    }
+    acc += __ldg(b + co);
+    out[idx] = acc > 0.f ? acc : 0.f;
+}
+
+template <int IH, int IW, int C>
+__global__ void __launch_bounds__(256) cnn_maxpool2_simt(const float *__restrict__ in, float *__restrict__ out,
+                                                         int n_patches)
+{
+    constexpr int OH = IH / 2, OW = IW / 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_patches * OH * OW * C) return;
+    const int c = (int)(idx % C);
+    long long t = idx / C;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int p = (int)(t / OH);
+    const float *q = in + ((size_t)p * IH * IW + (size_t)(2 * oy) * IW + 2 * ox) * C + c;
+    out[idx] = fmaxf(fmaxf(q[0], q[C]), fmaxf(q[(size_t)IW * C], q[(size_t)IW * C + C]));
+}
+
+template <int NIN, int NOUT, bool RELU>
+__global__ void __launch_bounds__(256) cnn_dense_simt(const float *__restrict__ in, const float *__restrict__ w,
+                                                      const float *__restrict__ b, float *__restrict__ out,
+                                                      int n_patches)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_patches * NOUT) return;
+    const int o = (int)(idx % NOUT);
+    const int p = (int)(idx / NOUT);
+    const float *ip = in + (size_t)p * NIN;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < NIN; i++) acc = fmaf(__ldg(ip + i), __ldg(w + (size_t)i * NOUT + o), acc);
+    acc += __ldg(b + o);
+    out[idx] = RELU ? (acc > 0.f ? acc : 0.f) : acc;
+}
+
+// ---------------------------------------------------------------------------------------------------- softmax + decode
+// One warp per region: softmax over 81 logits, then label = argmax (first maximum, as np.argmax), confidence =
+// max(y) / sum(y) with Python's sequential float32 sum (nn_cache.py:28-30). One thread per intersection then applies
+// the write order of predict_all_stones (regions in i, j order: region 9 overwrites row / column 17 of region 8).
+__global__ void __launch_bounds__(128) cnn_softmax_label(const float *__restrict__ logits, int n_regions,
+                                                         float *__restrict__ softmax, int *__restrict__ label,
+                                                         float *__restrict__ conf)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_regions) return;
+    const float *z = logits + (size_t)warp * CNN_F6;
+    float v[3];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int o = lane + 32 * k;
+        v[k] = o < CNN_F6 ? z[o] : -INFINITY;
+        m = fmaxf(m, v[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        v[k] = (lane + 32 * k) < CNN_F6 ? expf(v[k] - m) : 0.f;
+        s += v[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float *y = softmax + (size_t)warp * CNN_F6;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int o = lane + 32 * k;
+        if (o < CNN_F6) y[o] = __fdiv_rn(v[k], s);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int best = 0;
+        float bv = y[0], tot = 0.f;
+        for (int o = 0; o < CNN_F6; o++) {
+            const float t = y[o];
+            if (t > bv) { bv = t; best = o; }
+            tot = __fadd_rn(tot, t);
+        }
+        label[warp] = best;
+        conf[warp] = __fdiv_rn(bv, tot);
+    }
+}
+
+__global__ void __launch_bounds__(128) cnn_decode_board(const int *__restrict__ label, const float *__restrict__ conf,
+                                                        int n_frames, uint8_t *__restrict__ stones,
+                                                        float *__restrict__ conf_out, uint8_t *__restrict__ keep)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_frames * 361) return;
+    const int f = idx / 361, q = idx % 361, r = q / 19, c = q % 19;
+    const int i = r < 17 ? r >> 1 : 9, j = c < 17 ? c >> 1 : 9;   // last region that writes (r, c)
+    const int a = r - (i < 9 ? 2 * i : 17), b = c - (j < 9 ? 2 * j : 17);
+    const int reg = f * 100 + i * 10 + j;
+    int k = label[reg];
+    const int pw = a * 2 + b;  // base-3 digit index (nn_manager.py:236-254)
+    for (int t = 0; t < pw; t++) k /= 3;
+    const uint8_t s = (uint8_t)(k % 3);
+    const float cf = conf[reg];
+    if (stones) stones[idx] = s;
+    if (conf_out) conf_out[idx] = cf;
+    if (keep) keep[idx] = (s != CKB_E && cf > 0.6f) ? 1 : 0;
+}
+
+// d_softmax_tmp: n*100*81 floats used when the caller does not want the softmax; d_lab / d_cf live behind it
+int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softmax_or_null, float *d_softmax_tmp,
+                      uint8_t *d_stones, float *d_conf, uint8_t *d_keep, cudaStream_t st)
+{
+    const int nreg = n * 100;
+    float *sm = d_softmax_or_null ? d_softmax_or_null : d_softmax_tmp;
+    int *lab = (int *)(d_softmax_tmp + (size_t)nreg * CNN_F6);
+    float *cf = (float *)(lab + nreg);
+    cnn_softmax_label<<<(nreg * 32 + 127) / 128, 128, 0, st>>>(d_logits, nreg, sm, lab, cf);
+    CKB_LAUNCH_CHECK(ctx, "cnn_softmax_label");
+    cnn_decode_board<<<(n * 361 + 127) / 128, 128, 0, st>>>(lab, cf, n, d_stones, d_conf, d_keep);
+    CKB_LAUNCH_CHECK(ctx, "cnn_decode_board");
+    return CKB_OK;
+}
+
+// workspace of the SIMT path, floats per patch
+#define SIMT_PER_PATCH (CNN_A1 + CNN_A2 + CNN_P2 + CNN_A3 + CNN_A4 + CNN_P4 + CNN_F5 + CNN_F6 + CNN_F6 + 2)
+
+size_t ckb_cnn_simt_workspace(int n) { return (size_t)n * 100 * SIMT_PER_PATCH * sizeof(float) + 256; }
+
+static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
+
+extern "C" int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes,
+                                    float *d_softmax, uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream)
+{
+    if (!ctx) return CKB_E_INVALID;
+    if (!ctx->cnn) CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_forward_simt: call ckb_set_cnn_weights first");
+    if (!d_goban || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward_simt: bad argument");
+    if (work_bytes < ckb_cnn_simt_workspace(n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_cnn_forward_simt: workspace too small");
+    if (n == 0) return CKB_OK;
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = n * 100;
+    const float *w = ctx->cnn->d_params;
+    float *a1 = (float *)d_work;
+    float *a2 = a1 + (size_t)P * CNN_A1;
+    float *p2 = a2 + (size_t)P * CNN_A2;
+    float *a3 = p2 + (size_t)P * CNN_P2;
+    float *a4 = a3 + (size_t)P * CNN_A3;
+    float *p4 = a4 + (size_t)P * CNN_A4;
+    float *f5 = p4 + (size_t)P * CNN_P4;
+    float *f6 = f5 + (size_t)P * CNN_F5;
+    float *tmp = f6 + (size_t)P * CNN_F6;
+    cnn_conv_relu_simt<5, 5, 3, 32, 40, 40, true><<<blocks_for((long long)P * CNN_A1), 256, 0, st>>>(d_goban, w + OFF_W1, w + OFF_B1, a1, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_conv1_simt");
+    cnn_conv_relu_simt<5, 5, 32, 32, 36, 36, false><<<blocks_for((long long)P * CNN_A2), 256, 0, st>>>(a1, w + OFF_W2, w + OFF_B2, a2, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_conv2_simt");
+    cnn_maxpool2_simt<32, 32, 32><<<blocks_for((long long)P * CNN_P2), 256, 0, st>>>(a2, p2, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_pool2_simt");
+    cnn_conv_relu_simt<3, 3, 32, 90, 16, 16, false><<<blocks_for((long long)P * CNN_A3), 256, 0, st>>>(p2, w + OFF_W3, w + OFF_B3, a3, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_conv3_simt");
+    cnn_conv_relu_simt<3, 3, 90, 90, 14, 14, false><<<blocks_for((long long)P * CNN_A4), 256, 0, st>>>(a3, w + OFF_W4, w + OFF_B4, a4, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_conv4_simt");
+    cnn_maxpool2_simt<12, 12, 90><<<blocks_for((long long)P * CNN_P4), 256, 0, st>>>(a4, p4, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_pool4_simt");
+    cnn_dense_simt<3240, 160, true><<<blocks_for((long long)P * CNN_F5), 256, 0, st>>>(p4, w + OFF_W5, w + OFF_B5, f5, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_fc1_simt");
+    cnn_dense_simt<160, 81, false><<<blocks_for((long long)P * CNN_F6), 256, 0, st>>>(f5, w + OFF_W6, w + OFF_B6, f6, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_fc2_simt");
+    return ckb_launch_decode(ctx, f6, n, d_softmax, tmp, d_stones, d_conf, d_keep, st);
+}

@@ -1,0 +1,661 @@
+// K3 + K2 — OpenCV-compatible 3-means colour clustering of the canonical goban image and the per-intersection
+// classification that follows it.
+//
+// Replaces SfClustering.find_stones (src/camkifu/stone/sf_clustering.py:48-178):
+//   cv2.kmeans(pixels, 3, None, (TERM_CRITERIA_EPS, 15, 3), 3, KMEANS_PP_CENTERS)                      :103-104
+//   labels+1, *mask, 361 x np.unique -> ratios (uint8 percentages)                                     :105-129
+//   interpret_ratios (centre grey -> B/E/W, argmax) and check_density                                  :131-178
+//
+// Parity design. cv2.kmeans' result depends on (a) the cv::RNG stream (multiply-with-carry), (b) k-means++ seeding:
+// float32 squared distances, float64 running sums, a sequential "p -= dist[i]" sampling scan, best of 3 trials,
+// (c) Lloyd iterations whose centre update is a SEQUENTIAL float32 sum in pixel order, (d) the stop rule
+// max centre shift^2 <= 9 with labels NOT re-assigned on the last iteration, (e) best of 3 attempts by compactness.
+// All of it is reproduced bit for bit. Distances and all the independent per-pixel work run in parallel; float64
+// sums are taken in a fixed (deterministic) tree order — they are exact whenever OpenCV's are, which holds for pixel
+// data (float32 terms spanning < 29 binades) — and the one inherently serial piece, the float32 centre sums, is
+// executed serially: the CTA computes the labels of a 512-pixel chunk in parallel, writes the per-(cluster, channel)
+// masked values to shared memory, and nine lanes of warp 0 then walk the chunk in pixel order with one dependent
+// FADD per pixel each (adding +0 for non-members is exact). The dependent-add latency (4 cycles) bounds an iteration
+// at ~0.3 ms for a whole board, so throughput comes from running many (frame, attempt) CTAs side by side: grid =
+// 3 attempts x n frames, 256 threads, 8 CTAs per SM.
+//
+// Kernels:  ckb_pack_region_*   region pixels -> linear, vector-loadable scratch (uchar4 / float4 per pixel)
+//           ckb_kmeans_attempt  one CTA per (frame, attempt)
+//           ckb_zone_classify   one CTA per frame: best attempt, labels, zone histograms (warp per zone, ballot/popc
+//                               reductions), ratios, stones, density check
+#include <float.h>
+
+#include "ckb_common.cuh"
+
+#define KM_THREADS 256
+#define KM_WARPS (KM_THREADS / 32)
+#define KM_SEG 256                     // pixels per warp segment in the k-means++ passes
+#define KM_MAX_N (380 * 380)
+#define KM_MAX_SEG ((KM_MAX_N + KM_SEG - 1) / KM_SEG)   // 565
+#define KM_CH 512                      // pixels per Lloyd chunk
+#define KM_PLANE (KM_CH + 4)           // +4 words: the nine lanes' 128-bit reads fall in distinct banks
+#define KM_MAX_ITER 100                // criteria type has EPS only => maxCount = 100 (the "15" is ignored)
+#define KM_EPS2 9.0                    // (eps = 3)^2
+
+struct KmAttempt {
+    double compactness;
+    float centers[9];      // final centres
+    float old_centers[9];  // the centres the returned labels were assigned against
+    int n_fix;             // empty-cluster repairs of the last iteration (label overrides)
+    int fix_idx[2];
+    int fix_k[2];
+    int iters;
+};
+
+struct Region {
+    int x0, y0, h, w, N;
+};
+
+// ----------------------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    // hal::normL2Sqr_ for n = 3: ((t0*t0 + t1*t1) + t2*t2) in float32 without contraction
+    const float t0 = __fsub_rn(ax, bx), t1 = __fsub_rn(ay, by), t2 = __fsub_rn(az, bz);
+    float d = __fmul_rn(t0, t0);
+    d = __fadd_rn(d, __fmul_rn(t1, t1));
+    d = __fadd_rn(d, __fmul_rn(t2, t2));
+    return d;
+}
+
+template <bool F32>
+__device__ __forceinline__ float3 load_px(const void *scratch, int i)
+{
+    if (F32) {
+        const float4 v = __ldg((const float4 *)scratch + i);
+        return make_float3(v.x, v.y, v.z);
+    } else {
+        const uchar4 v = __ldg((const uchar4 *)scratch + i);
+        return make_float3((float)v.x, (float)v.y, (float)v.z);
+    }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_incl_scan_d(double v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t rng_next(uint64_t &s)
+{
+    s = (uint64_t)(uint32_t)s * 4164903690ULL + (s >> 32);
+    return (uint32_t)s;
+}
+
+__device__ __forceinline__ double rng_double(uint64_t &s)
+{
+    const uint32_t t = rng_next(s);
+    const uint64_t v = ((uint64_t)t << 32) | rng_next(s);
+    return __dmul_rn(__ull2double_rn(v), 5.4210108624275221700372640043497e-20);
+}
+
+// label = first minimum of the three float32 distances (KMeansDistanceComputer: `if (min_dist > dist)`)
+__device__ __forceinline__ int argmin3(float3 x, const float *c)
+{
+    const float d0 = dist3(x.x, x.y, x.z, c[0], c[1], c[2]);
+    const float d1 = dist3(x.x, x.y, x.z, c[3], c[4], c[5]);
+    const float d2 = dist3(x.x, x.y, x.z, c[6], c[7], c[8]);
+    int k = 0;
+    float m = d0;
+    if (m > d1) { m = d1; k = 1; }
+    if (m > d2) { k = 2; }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------------------- pack
+template <bool F32>
+__global__ void __launch_bounds__(256) ckb_pack_region(const void *__restrict__ imgs, int S, Region rg,
+                                                       void *__restrict__ scratch, size_t scratch_stride)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rg.N) return;
+    const int row = i / rg.w, col = i - row * rg.w;
+    const size_t src = ((size_t)f * S * S + (size_t)(rg.x0 + row) * S + rg.y0 + col) * 3;
+    char *dst = (char *)scratch + (size_t)f * scratch_stride;
+    if (F32) {
+        const float *p = (const float *)imgs + src;
+        ((float4 *)dst)[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    } else {
+        const uint8_t *p = (const uint8_t *)imgs + src;
+        ((uchar4 *)dst)[i] = make_uchar4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- k-means attempt
+struct __align__(16) KmShared {
+    union {
+        double segsum[4][KM_MAX_SEG + 3];  // [0] current dist, [1..3] the three trial candidates   (k-means++)
+        float planes[9][KM_PLANE];         // masked values per (cluster, channel) of one chunk     (Lloyd)
+    } u;
+    double red_d[KM_WARPS * 3];
+    int red_i[KM_WARPS * 4];
+    float cen[9];
+    float oldc[9];
+    float sums[9];
+    int cnt[3];
+    int cand[3];
+    int fix_idx[2];
+    int fix_k[2];
+    int n_fix;
+    int flag;
+    double dtmp[4];
+};
+
+// nearest already-chosen centre distance (k-means++ "dist" array, recomputed instead of stored)
+__device__ __forceinline__ float pp_base(float3 x, const float *cen, int ncen)
+{
+    float b = dist3(x.x, x.y, x.z, cen[0], cen[1], cen[2]);
+    if (ncen > 1) {
+        const float d1 = dist3(x.x, x.y, x.z, cen[3], cen[4], cen[5]);
+        b = d1 < b ? d1 : b;  // std::min(d, dist[i])
+    }
+    return b;
+}
+
+template <bool F32>
+__device__ int pp_sample(const void *px, int N, int nseg, const double *segsum, double p, const float *cen, int ncen,
+                         int lane)
+{
+    // first index ci in [0, N-1) with p - sum_{i<=ci} dist[i] <= 0, else N-1   (generateCentersPP)
+    const int per = (nseg + 31) >> 5;
+    const int s0 = lane * per, s1 = min(nseg, s0 + per);
+    double loc = 0.0;
+    for (int s = s0; s < s1; s++) loc += segsum[s];
+    const double incl = warp_incl_scan_d(loc, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+    double r = p - excl;
+    int found = -1;
+    double r_before = 0.0;
+    for (int s = s0; s < s1; s++) {
+        const double rb = r;
+        r -= segsum[s];
+        if (r <= 0.0) { found = s; r_before = rb; break; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, found >= 0);
+    if (bal == 0u) return N - 1;
+    const int src = __ffs(bal) - 1;
+    const int seg = __shfl_sync(0xffffffffu, found, src);
+    double resid = __shfl_sync(0xffffffffu, r_before, src);
+    int ci = min(N - 1, seg * KM_SEG + KM_SEG - 1);
+    for (int j = 0; j < KM_SEG / 32; j++) {
+        const int i = seg * KM_SEG + j * 32 + lane;
+        double d = 0.0;
+        if (i < N) d = (double)pp_base(load_px<F32>(px, i), cen, ncen);
+        const double pre = warp_incl_scan_d(d, lane);
+        const unsigned hit = __ballot_sync(0xffffffffu, (i < N) && (resid - pre <= 0.0));
+        if (hit) { ci = seg * KM_SEG + j * 32 + (__ffs(hit) - 1); break; }
+        resid -= __shfl_sync(0xffffffffu, pre, 31);
+    }
+    return min(ci, N - 1);
+}
+
+// one k-means++ pass: for ncand candidate centres (pixel indices in sh.cand) compute min(d(x, cand), base) summed per
+// segment into segsum[1 + c][seg]; ncen == 0 means "no base" (the very first centre).
+template <bool F32>
+__device__ void pp_pass(const void *px, int N, int nseg, KmShared &sh, int ncen, int ncand, int warp, int lane)
+{
+    float3 cd[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) cd[c] = load_px<F32>(px, sh.cand[c < ncand ? c : 0]);
+    for (int seg = warp; seg < nseg; seg += KM_WARPS) {
+        double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < KM_SEG / 32; j++) {
+            const int i = seg * KM_SEG + j * 32 + lane;
+            if (i < N) {
+                const float3 x = load_px<F32>(px, i);
+                const float base = ncen > 0 ? pp_base(x, sh.cen, ncen) : FLT_MAX;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (c < ncand) {
+                        const float d = dist3(x.x, x.y, x.z, cd[c].x, cd[c].y, cd[c].z);
+                        acc[c] += (double)(ncen > 0 ? (d < base ? d : base) : d);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (c < ncand) {
+                const double s = warp_sum_d(acc[c]);
+                if (lane == 0) sh.u.segsum[1 + c][seg] = s;
+            }
+        }
+    }
+    __syncthreads();
+    // totals: warp c sums the candidate-c segment sums
+    if (warp < ncand) {
+        double t = 0.0;
+        for (int s = lane; s < nseg; s += 32) t += sh.u.segsum[1 + warp][s];
+        t = warp_sum_d(t);
+        if (lane == 0) sh.dtmp[1 + warp] = t;
+    }
+    __syncthreads();
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__restrict__ scratch,
+                                                                 size_t scratch_stride, int N,
+                                                                 const uint64_t *__restrict__ rng_states,
+                                                                 KmAttempt *__restrict__ results)
+{
+    __shared__ KmShared sh;
+    const int attempt = blockIdx.x, frame = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const void *px = (const char *)scratch + (size_t)frame * scratch_stride;
+    const int nseg = (N + KM_SEG - 1) / KM_SEG;
+
+    // ---- cv::RNG draws of this attempt: 1 integer + 6 doubles = 13 draws
+    uint64_t st = rng_states[frame];
+    for (int k = 0; k < 13 * attempt; k++) rng_next(st);
+    const int c0 = (int)(rng_next(st) % (uint32_t)N);
+    double u[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) u[k] = rng_double(st);
+
+    // ---- k-means++ seeding
+    if (tid == 0) { sh.cand[0] = c0; sh.cand[1] = c0; sh.cand[2] = c0; }
+    __syncthreads();
+    pp_pass<F32>(px, N, nseg, sh, 0, 1, warp, lane);
+    if (tid < 3) {
+        const float3 x = load_px<F32>(px, c0);
+        sh.cen[tid] = tid == 0 ? x.x : (tid == 1 ? x.y : x.z);
+    }
+    for (int s = tid; s < nseg; s += KM_THREADS) sh.u.segsum[0][s] = sh.u.segsum[1][s];
+    if (tid == 0) sh.dtmp[0] = sh.dtmp[1];  // sum0
+    __syncthreads();
+    for (int k = 1; k < 3; k++) {
+        if (warp < 3) {
+            const double p = __dmul_rn(u[(k - 1) * 3 + warp], sh.dtmp[0]);
+            const int ci = pp_sample<F32>(px, N, nseg, sh.u.segsum[0], p, sh.cen, k, lane);
+            if (lane == 0) sh.cand[warp] = ci;
+        }
+        __syncthreads();
+        pp_pass<F32>(px, N, nseg, sh, k, 3, warp, lane);
+        // best trial: strict '<' in trial order
+        int best = 0;
+        double bs = sh.dtmp[1];
+        if (sh.dtmp[2] < bs) { bs = sh.dtmp[2]; best = 1; }
+        if (sh.dtmp[3] < bs) { bs = sh.dtmp[3]; best = 2; }
+        __syncthreads();
+        if (tid < 3) {
+            const float3 x = load_px<F32>(px, sh.cand[best]);
+            sh.cen[3 * k + tid] = tid == 0 ? x.x : (tid == 1 ? x.y : x.z);
+        }
+        for (int s = tid; s < nseg; s += KM_THREADS) sh.u.segsum[0][s] = sh.u.segsum[1 + best][s];
+        if (tid == 0) sh.dtmp[0] = bs;
+        __syncthreads();
+    }
+
+    // ---- Lloyd iterations
+    const int nchunk = (N + KM_CH - 1) / KM_CH;
+    int iter = 1;  // iteration 0 was the seeding; labels are (conceptually) assigned against sh.cen
+    for (;;) {
+        if (tid < 9) sh.oldc[tid] = sh.cen[tid];
+        if (tid == 0) sh.n_fix = 0;
+        __syncthreads();
+        float oc[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) oc[k] = sh.oldc[k];
+
+        // centre sums: parallel labelling per chunk, then the sequential float32 adds on nine lanes of warp 0
+        float acc = 0.f;
+        int c0n = 0, c1n = 0, c2n = 0;
+        float3 xn[2];
+        bool vn[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = q * KM_THREADS + tid;
+            vn[q] = i < N;
+            xn[q] = vn[q] ? load_px<F32>(px, i) : make_float3(0.f, 0.f, 0.f);
+        }
+        for (int ch = 0; ch < nchunk; ch++) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int p = q * KM_THREADS + tid;
+                const float3 x = xn[q];
+                const int lab = vn[q] ? argmin3(x, oc) : -1;
+                c0n += lab == 0;
+                c1n += lab == 1;
+                c2n += lab == 2;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const bool m = lab == k;
+                    sh.u.planes[3 * k + 0][p] = m ? x.x : 0.f;
+                    sh.u.planes[3 * k + 1][p] = m ? x.y : 0.f;
+                    sh.u.planes[3 * k + 2][p] = m ? x.z : 0.f;
+                }
+                const int i = (ch + 1) * KM_CH + p;  // prefetch the next chunk while warp 0 runs the serial sums
+                vn[q] = i < N;
+                xn[q] = vn[q] ? load_px<F32>(px, i) : make_float3(0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            if (warp == 0 && lane < 9) {
+                const float4 *pl = (const float4 *)sh.u.planes[lane];
+#pragma unroll 8
+                for (int p = 0; p < KM_CH / 4; p++) {
+                    const float4 v = pl[p];
+                    acc = __fadd_rn(acc, v.x);
+                    acc = __fadd_rn(acc, v.y);
+                    acc = __fadd_rn(acc, v.z);
+                    acc = __fadd_rn(acc, v.w);
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0 && lane < 9) sh.sums[lane] = acc;
+        // counts
+        c0n = __reduce_add_sync(0xffffffffu, c0n);
+        c1n = __reduce_add_sync(0xffffffffu, c1n);
+        c2n = __reduce_add_sync(0xffffffffu, c2n);
+        if (lane == 0) { sh.red_i[warp * 4 + 0] = c0n; sh.red_i[warp * 4 + 1] = c1n; sh.red_i[warp * 4 + 2] = c2n; }
+        __syncthreads();
+        if (tid < 3) {
+            int t = 0;
+            for (int w = 0; w < KM_WARPS; w++) t += sh.red_i[w * 4 + tid];
+            sh.cnt[tid] = t;
+        }
+        __syncthreads();
+
+        // empty-cluster repair (rare): move the farthest point of the biggest cluster into the empty one
+        for (int k = 0; k < 3; k++) {
+            if (sh.cnt[k] != 0) continue;  // block-uniform
+            int max_k = 0;
+            for (int k1 = 1; k1 < 3; k1++) if (sh.cnt[max_k] < sh.cnt[k1]) max_k = k1;
+            const float scale = __fdiv_rn(1.f, (float)sh.cnt[max_k]);
+            const float bx = __fmul_rn(sh.sums[3 * max_k], scale), by = __fmul_rn(sh.sums[3 * max_k + 1], scale),
+                        bz = __fmul_rn(sh.sums[3 * max_k + 2], scale);
+            // farthest: `if (max_dist <= dist)` in index order => largest distance, last index among ties
+            float bestd = -1.f;
+            int besti = -1;
+            for (int i = tid; i < N; i += KM_THREADS) {
+                const float3 x = load_px<F32>(px, i);
+                int lab = argmin3(x, oc);
+                for (int q = 0; q < sh.n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
+                if (lab != max_k) continue;
+                const float d = dist3(x.x, x.y, x.z, bx, by, bz);
+                if (d > bestd || (d == bestd && i > besti)) { bestd = d; besti = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bestd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (od > bestd || (od == bestd && oi > besti)) { bestd = od; besti = oi; }
+            }
+            if (lane == 0) { sh.red_d[warp] = (double)bestd; sh.red_i[warp] = besti; }
+            __syncthreads();
+            if (tid == 0) {
+                double bd = sh.red_d[0];
+                int bi = sh.red_i[0];
+                for (int w = 1; w < KM_WARPS; w++)
+                    if (sh.red_d[w] > bd || (sh.red_d[w] == bd && sh.red_i[w] > bi)) { bd = sh.red_d[w]; bi = sh.red_i[w]; }
+                const float3 x = load_px<F32>(px, bi);
+                sh.cnt[max_k]--;
+                sh.cnt[k]++;
+                sh.fix_idx[sh.n_fix] = bi;
+                sh.fix_k[sh.n_fix] = k;
+                sh.n_fix++;
+                sh.sums[3 * max_k + 0] = __fsub_rn(sh.sums[3 * max_k + 0], x.x);
+                sh.sums[3 * max_k + 1] = __fsub_rn(sh.sums[3 * max_k + 1], x.y);
+                sh.sums[3 * max_k + 2] = __fsub_rn(sh.sums[3 * max_k + 2], x.z);
+                sh.sums[3 * k + 0] = __fadd_rn(sh.sums[3 * k + 0], x.x);
+                sh.sums[3 * k + 1] = __fadd_rn(sh.sums[3 * k + 1], x.y);
+                sh.sums[3 * k + 2] = __fadd_rn(sh.sums[3 * k + 2], x.z);
+            }
+            __syncthreads();
+        }
+
+        // new centres, shift, stop rule
+        if (tid == 0) {
+            double max_shift = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const float scale = __fdiv_rn(1.f, (float)sh.cnt[k]);
+                double dist = 0.0;
+                for (int j = 0; j < 3; j++) {
+                    const float c = __fmul_rn(sh.sums[3 * k + j], scale);
+                    sh.cen[3 * k + j] = c;
+                    const double t = (double)__fsub_rn(c, sh.oldc[3 * k + j]);
+                    dist = __dadd_rn(dist, __dmul_rn(t, t));
+                }
+                max_shift = dist > max_shift ? dist : max_shift;
+            }
+            ++iter;
+            sh.flag = (iter == KM_MAX_ITER) || (max_shift <= KM_EPS2);
+        } else {
+            ++iter;
+        }
+        __syncthreads();
+        if (sh.flag) break;
+    }
+
+    // ---- compactness: labels stay those assigned against oldc (+ repairs); distances to the final centres
+    {
+        float oc[9], nc[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) { oc[k] = sh.oldc[k]; nc[k] = sh.cen[k]; }
+        double acc = 0.0;
+        for (int i = tid; i < N; i += KM_THREADS) {
+            const float3 x = load_px<F32>(px, i);
+            int lab = argmin3(x, oc);
+            for (int q = 0; q < sh.n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
+            acc += (double)dist3(x.x, x.y, x.z, nc[3 * lab], nc[3 * lab + 1], nc[3 * lab + 2]);
+        }
+        acc = warp_sum_d(acc);
+        if (lane == 0) sh.red_d[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < KM_WARPS; w++) t += sh.red_d[w];
+            KmAttempt &r = results[frame * 3 + attempt];
+            r.compactness = t;
+            for (int k = 0; k < 9; k++) { r.centers[k] = sh.cen[k]; r.old_centers[k] = sh.oldc[k]; }
+            r.n_fix = sh.n_fix;
+            for (int q = 0; q < 2; q++) { r.fix_idx[q] = sh.fix_idx[q]; r.fix_k[q] = sh.fix_k[q]; }
+            r.iters = iter;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ zone classification
+__device__ __forceinline__ int center_grey(const float *c)
+{
+    // int(sum(x) / 3) over numpy float32 scalars (sf_clustering.py:107,148): float32 adds, float32 divide, truncate
+    float s = __fadd_rn(0.f, c[0]);
+    s = __fadd_rn(s, c[1]);
+    s = __fadd_rn(s, c[2]);
+    return (int)__fdiv_rn(s, 3.0f);
+}
+
+#define ZC_THREADS 1024
+template <bool F32>
+__global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__restrict__ scratch, size_t scratch_stride,
+                                                                Region rg, int gsize, int rs, int re, int cs, int ce,
+                                                                const KmAttempt *__restrict__ results,
+                                                                const int32_t *__restrict__ rects,
+                                                                const uint8_t *__restrict__ mask, int S,
+                                                                uint8_t *__restrict__ stones_out,
+                                                                uint8_t *__restrict__ trusted_out,
+                                                                uint8_t *__restrict__ ratios_out,
+                                                                float *__restrict__ centers_out,
+                                                                double *__restrict__ compact_out,
+                                                                int32_t *__restrict__ labels_out)
+{
+    __shared__ uint8_t s_stones[CKB_MAX_ZONES];
+    __shared__ int s_hist[3];
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const void *px = (const char *)scratch + (size_t)frame * scratch_stride;
+
+    // best attempt: `if (compactness < best_compactness)` in attempt order, starting from DBL_MAX
+    int best = 0;
+    double bc = DBL_MAX;
+    for (int a = 0; a < 3; a++) {
+        const double c = results[frame * 3 + a].compactness;
+        if (c < bc) { bc = c; best = a; }
+    }
+    const KmAttempt &R = results[frame * 3 + best];
+    float oc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) oc[k] = R.old_centers[k];
+    const int n_fix = R.n_fix;
+    const int f0 = R.fix_idx[0], f1 = R.fix_idx[1], fk0 = R.fix_k[0], fk1 = R.fix_k[1];
+
+    int cv[3];
+    for (int k = 0; k < 3; k++) cv[k] = center_grey(R.centers + 3 * k);
+    const int mn = min(cv[0], min(cv[1], cv[2])), mx = max(cv[0], max(cv[1], cv[2]));
+    const int med = cv[0] + cv[1] + cv[2] - mn - mx;
+    const int mid = cv[0] == med ? 0 : (cv[1] == med ? 1 : 2);  // centers_val.index(sorted(centers_val)[1])
+    uint8_t col[3];
+    for (int k = 0; k < 3; k++) col[k] = cv[k] == mn ? CKB_B : (cv[k] == mx ? CKB_W : CKB_E);
+
+    if (tid < 3) s_hist[tid] = 0;
+    if (tid == 0) {
+        if (centers_out) for (int k = 0; k < 9; k++) centers_out[frame * 9 + k] = R.centers[k];
+        if (compact_out) compact_out[frame] = bc;
+    }
+    const int nz = gsize * gsize;
+    for (int z = warp; z < nz; z += ZC_THREADS / 32) {
+        const int zr = z / gsize, zc = z - zr * gsize;
+        uint8_t r3[3] = {0, 0, 0};
+        r3[mid] = 1;
+        uint8_t stone = CKB_E;
+        if (zr >= rs && zr < re && zc >= cs && zc < ce) {
+            const int a0 = rects[z * 4 + 0], b0 = rects[z * 4 + 1], a1 = rects[z * 4 + 2], b1 = rects[z * 4 + 3];
+            const int zw = b1 - b0, total = (a1 - a0) * zw;
+            int c0n = 0, c1n = 0, c2n = 0;
+            for (int t = lane; t < total; t += 32) {
+                const int i = a0 + t / zw, j = b0 + t % zw;
+                if (mask[(size_t)i * S + j]) {
+                    const int li = (i - rg.x0) * rg.w + (j - rg.y0);
+                    int lab = argmin3(load_px<F32>(px, li), oc);
+                    if (n_fix > 0 && li == f0) lab = fk0;
+                    if (n_fix > 1 && li == f1) lab = fk1;
+                    c0n += lab == 0;
+                    c1n += lab == 1;
+                    c2n += lab == 2;
+                }
+            }
+            c0n = __reduce_add_sync(0xffffffffu, c0n);
+            c1n = __reduce_add_sync(0xffffffffu, c1n);
+            c2n = __reduce_add_sync(0xffffffffu, c2n);
+            // uint8(100 * count / zone_pixels), written only for labels that are present
+            if (c0n) r3[0] = (uint8_t)((100 * c0n) / total);
+            if (c1n) r3[1] = (uint8_t)((100 * c1n) / total);
+            if (c2n) r3[2] = (uint8_t)((100 * c2n) / total);
+            int b = 0;
+            if (r3[1] > r3[b]) b = 1;
+            if (r3[2] > r3[b]) b = 2;
+            stone = col[b];
+        }
+        if (lane == 0) {
+            s_stones[z] = stone;
+            if (stones_out) stones_out[(size_t)frame * nz + z] = stone;
+            if (ratios_out) {
+                uint8_t *o = ratios_out + ((size_t)frame * nz + z) * 3;
+                o[0] = r3[0]; o[1] = r3[1]; o[2] = r3[2];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nz) atomicAdd(&s_hist[s_stones[tid]], 1);
+    __syncthreads();
+    // check_density: three distinct values, each seen at least twice (sf_clustering.py:170-178)
+    if (tid == 0 && trusted_out) trusted_out[frame] = (s_hist[0] >= 2 && s_hist[1] >= 2 && s_hist[2] >= 2) ? 1 : 0;
+
+    if (labels_out) {
+        int32_t *lo = labels_out + (size_t)frame * rg.N;
+        for (int i = tid; i < rg.N; i += ZC_THREADS) {
+            int lab = argmin3(load_px<F32>(px, i), oc);
+            if (n_fix > 0 && i == f0) lab = fk0;
+            if (n_fix > 1 && i == f1) lab = fk1;
+            lo[i] = lab;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------- launcher
+int ckb_kmeans_init_tables(ckb_ctx *ctx)
+{
+    (void)ctx;
+    return CKB_OK;
+}
+
+static Region make_region(const ckb_ctx *ctx, int rs, int re, int cs, int ce)
+{
+    // cluster_colors: x0, y0 = getrect(rs, cs)[:2]; x1, y1 = getrect(re-1, ce-1)[2:]   (sf_clustering.py:99-101)
+    const int g = ctx->gsize;
+    Region r;
+    r.x0 = ctx->h_rects[(rs * g + cs) * 4 + 0];
+    r.y0 = ctx->h_rects[(rs * g + cs) * 4 + 1];
+    r.h = ctx->h_rects[((re - 1) * g + (ce - 1)) * 4 + 2] - r.x0;
+    r.w = ctx->h_rects[((re - 1) * g + (ce - 1)) * 4 + 3] - r.y0;
+    r.N = r.h * r.w;
+    return r;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" size_t ckb_find_stones_workspace(const ckb_ctx *ctx, int n)
+{
+    if (!ctx || n < 0) return 0;
+    const size_t per_frame = align_up((size_t)ctx->S * ctx->S * 16, 256);
+    return (size_t)n * per_frame + align_up((size_t)n * 3 * sizeof(KmAttempt), 256) + 256;
+}
+
+extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, int rs, int re, int cs, int ce,
+                               const uint64_t *d_rng_states, void *d_work, size_t work_bytes, uint8_t *d_stones,
+                               uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness,
+                               int32_t *d_labels, void *stream)
+{
+    if (!ctx) return CKB_E_INVALID;
+    const int g = ctx->gsize;
+    if (!d_imgs || !d_rng_states || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: bad argument");
+    if (rs < 0 || cs < 0 || re > g || ce > g || rs >= re || cs >= ce)
+        CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: region [%d,%d)x[%d,%d) outside the %dx%d goban", rs, re, cs, ce, g, g);
+    if (work_bytes < ckb_find_stones_workspace(ctx, n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_find_stones: workspace too small");
+    if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: workspace must be 256-byte aligned");
+    if (n == 0) return CKB_OK;
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Region rg = make_region(ctx, rs, re, cs, ce);
+    const size_t stride = align_up((size_t)ctx->S * ctx->S * 16, 256);
+    KmAttempt *res = (KmAttempt *)((char *)d_work + (size_t)n * stride);
+    dim3 pgrid((rg.N + 255) / 256, n);
+    if (is_f32) {
+        ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
+        CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
+        ckb_kmeans_attempt<true><<<dim3(3, n), KM_THREADS, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
+        ckb_zone_classify<true><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
+                                                          ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
+                                                          d_centers, d_compactness, d_labels);
+        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
+    } else {
+        ckb_pack_region<false><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
+        CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
+        ckb_kmeans_attempt<false><<<dim3(3, n), KM_THREADS, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
+        ckb_zone_classify<false><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
+                                                           ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
+                                                           d_centers, d_compactness, d_labels);
+        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
+    }
+    return CKB_OK;
+}

@@ -1,0 +1,177 @@
+"""StoneEngine — host-side driver of the CUDA stone-detection path.
+
+Thin layer over the C ABI (include/camkifu_b200.h): PyTorch provides device buffers and the CUDA stream, every
+computation is a hand-written sm_100a kernel inside libcamkifu_b200.so. One engine = one `ckb_ctx` = one finder
+instance; it is safe to use from the finder's own thread (ctypes releases the GIL during calls).
+
+Colour codes: 0 = E, 1 = B, 2 = W (the reference's Golib constants 'E', 'B', 'W').
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CkbError
+
+DRAWS_PER_KMEANS = 39  # CKB_RNG_DRAWS_PER_KMEANS
+
+
+def rng_seed(seed: int) -> int:
+    """cv::RNG state installed by cv2.setRNGSeed(seed)."""
+    return int(_lib.lib().ckb_rng_seed(seed & 0xffffffff))
+
+
+def rng_advance(state: int, n_kmeans_calls: int) -> int:
+    """State after `n_kmeans_calls` cv2.kmeans(K=3, attempts=3, KMEANS_PP_CENTERS) calls."""
+    return int(_lib.lib().ckb_rng_advance(state, DRAWS_PER_KMEANS * n_kmeans_calls))
+
+
+class StoneEngine:
+    def __init__(self, gsize: int = 19, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("camkifu_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.gsize = gsize
+        self.S = 20 * gsize
+        h = C.c_void_p()
+        rc = self.L.ckb_create(C.byref(h), self.device.index or 0, gsize)
+        self._h = h
+        if rc != 0:
+            msg = self.L.ckb_last_error(h).decode() if h else "ckb_create failed"
+            if h:
+                self.L.ckb_destroy(h)
+            self._h = None
+            raise CkbError(rc, msg)
+        self._work = None
+        self.has_weights = False
+
+    # ------------------------------------------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.ckb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CkbError(rc, self.L.ckb_last_error(self._h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._work
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.ckb_launch_count(self._h))
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    # ------------------------------------------------------------------------------------------------------------ K1
+    def warp(self, frames: torch.Tensor, mtx, out: torch.Tensor = None) -> torch.Tensor:
+        """frames: uint8 [n, H, W, 3] (or [H, W, 3]) on the device; mtx: 3x3 or [n, 3, 3] float64 frame->canonical
+        homography (BoardFinder.mtx). Returns uint8 [n, S, S, 3] — cv2.warpPerspective(frame, mtx, (S, S)) per frame."""
+        if frames.dim() == 3:
+            frames = frames.unsqueeze(0)
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.shape[-1] == 3
+        assert frames.stride(3) == 1 and frames.stride(2) == 3, "frames must be interleaved BGR"
+        n, H, W, _ = frames.shape
+        m = np.ascontiguousarray(np.asarray(mtx, dtype=np.float64)).reshape(-1, 9)
+        if out is None:
+            out = torch.empty((n, self.S, self.S, 3), dtype=torch.uint8, device=self.device)
+        self._check(self.L.ckb_warp(self._h, self._ptr(frames), n, H, W, frames.stride(1), frames.stride(0) if n > 1
+                                    else frames.stride(1) * H, m.ctypes.data_as(C.c_void_p), m.shape[0], self._ptr(out),
+                                    self._stream()))
+        return out
+
+    def accumulate(self, goban: torch.Tensor, accu: torch.Tensor, first: bool, alpha: float = 0.2,
+                   snap_every: int = 0, snap_phase: int = 0):
+        """Running average of sf_clustering.py:33-36 applied to the n images in order. Returns the snapshots tensor
+        [k, S, S, 3] float32 for frames i with (i + snap_phase) % snap_every == 0 (None when snap_every == 0)."""
+        if goban.dim() == 3:
+            goban = goban.unsqueeze(0)
+        n = goban.shape[0]
+        assert goban.is_contiguous() and accu.is_contiguous() and accu.dtype == torch.float32
+        snaps = None
+        if snap_every > 0:
+            k = sum(1 for i in range(n) if (i + snap_phase) % snap_every == 0)
+            snaps = torch.empty((k, self.S, self.S, 3), dtype=torch.float32, device=self.device)
+        self._check(self.L.ckb_accumulate(self._h, self._ptr(goban), n, self._ptr(accu), alpha, int(first),
+                                          self._ptr(snaps), max(snap_every, 1), snap_phase, self._stream()))
+        return snaps
+
+    # ------------------------------------------------------------------------------------------------------- K3 + K2
+    def find_stones(self, imgs: torch.Tensor, rng_states, rs=0, re=None, cs=0, ce=None, want=("stones", "trusted")):
+        """SfClustering.find_stones on n canonical images (uint8 or float32 [n, S, S, 3]).
+        rng_states: n cv::RNG states (ints) — see rng_seed / rng_advance. Returns a dict of device tensors."""
+        g = self.gsize
+        re = g if re is None else re
+        ce = g if ce is None else ce
+        if imgs.dim() == 3:
+            imgs = imgs.unsqueeze(0)
+        assert imgs.is_contiguous() and imgs.shape[1:] == (self.S, self.S, 3)
+        assert imgs.dtype in (torch.uint8, torch.float32)
+        n = imgs.shape[0]
+        st = torch.as_tensor(np.asarray(rng_states, dtype=np.uint64).astype(np.int64), device=self.device)
+        assert st.numel() == n
+        dev = self.device
+        out = {"stones": torch.empty((n, g, g), dtype=torch.uint8, device=dev),
+               "trusted": torch.empty((n,), dtype=torch.uint8, device=dev)}
+        if "ratios" in want:
+            out["ratios"] = torch.empty((n, g, g, 3), dtype=torch.uint8, device=dev)
+        if "centers" in want:
+            out["centers"] = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        if "compactness" in want:
+            out["compactness"] = torch.empty((n,), dtype=torch.float64, device=dev)
+        if "labels" in want:
+            x0, y0 = 20 * rs, 20 * cs
+            x1 = self.S - 1 if re == g else 20 * re
+            y1 = self.S - 1 if ce == g else 20 * ce
+            out["labels"] = torch.empty((n, x1 - x0, y1 - y0), dtype=torch.int32, device=dev)
+        wb = self.L.ckb_find_stones_workspace(self._h, n)
+        work = self._workspace(wb)
+        self._check(self.L.ckb_find_stones(self._h, self._ptr(imgs), int(imgs.dtype == torch.float32), n, rs, re, cs,
+                                           ce, self._ptr(st), self._ptr(work), work.numel(), self._ptr(out["stones"]),
+                                           self._ptr(out["trusted"]), self._ptr(out.get("ratios")),
+                                           self._ptr(out.get("centers")), self._ptr(out.get("compactness")),
+                                           self._ptr(out.get("labels")), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------ K4
+    def set_cnn_weights(self, params: np.ndarray):
+        p = np.ascontiguousarray(params, dtype=np.float32).ravel()
+        self._check(self.L.ckb_set_cnn_weights(self._h, p.ctypes.data_as(C.c_void_p), p.size))
+        self.has_weights = True
+
+    def cnn_forward(self, goban: torch.Tensor, want_softmax: bool = True, simt: bool = False):
+        """NNCache.predict_all_stones + the 0.6 confidence rule on n canonical images (uint8 [n, 380, 380, 3]).
+        Returns dict(stones [n,19,19] u8, conf [n,19,19] f32, keep [n,19,19] u8, softmax [n,100,81] f32)."""
+        if goban.dim() == 3:
+            goban = goban.unsqueeze(0)
+        assert goban.is_contiguous() and goban.dtype == torch.uint8 and goban.shape[1:] == (380, 380, 3)
+        n = goban.shape[0]
+        dev = self.device
+        out = {"stones": torch.empty((n, 19, 19), dtype=torch.uint8, device=dev),
+               "conf": torch.empty((n, 19, 19), dtype=torch.float32, device=dev),
+               "keep": torch.empty((n, 19, 19), dtype=torch.uint8, device=dev)}
+        if want_softmax:
+            out["softmax"] = torch.empty((n, 100, 81), dtype=torch.float32, device=dev)
+        wb = self.L.ckb_cnn_workspace(self._h, n)
+        work = self._workspace(wb)
+        fn = self.L.ckb_cnn_forward_simt if simt else self.L.ckb_cnn_forward
+        self._check(fn(self._h, self._ptr(goban), n, self._ptr(work), work.numel(), self._ptr(out.get("softmax")),
+                       self._ptr(out["stones"]), self._ptr(out["conf"]), self._ptr(out["keep"]), self._stream()))
+        return out

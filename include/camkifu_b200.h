@@ -1,0 +1,131 @@
+/*
+ * camkifu_b200.h — C ABI of the B200-native (sm_100a) stone-detection hot path of CamKifu.
+ *
+ * The reference (ArnaudPel/CamKifu) has NO native interface: its plugin boundary is the Python class contract of
+ * camkifu.stone.StonesFinder (src/camkifu/stone/stonesfinder.py:18) and the arithmetic is done by cv2 / Keras calls.
+ * Each entry point below replaces one of those third-party calls (or the Python loop around it); the reference call
+ * site is cited on every function. The Python mirror of the plugin API that sits on top is camkifu_b200/plugins.py;
+ * INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CKB_E_* code on failure and never throws or aborts;
+ *     ckb_last_error(ctx) gives the message of the last failure on that context;
+ *   - the caller owns every device buffer (raw device pointers) and the CUDA stream (cudaStream_t passed as void*);
+ *     the library owns only the opaque context (constant tables, packed CNN weights);
+ *   - all work is enqueued on `stream` and is asynchronous with respect to the host; no function synchronises;
+ *   - one context per finder instance / thread; contexts share no mutable state;
+ *   - images are BGR uint8, interleaved, row-major (what cv2.VideoCapture hands the reference, vmanager.py:584);
+ *   - board colours are uint8 codes CKB_E / CKB_B / CKB_W (the reference's Golib constants 'E','B','W').
+ */
+#ifndef CAMKIFU_B200_H
+#define CAMKIFU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CKB_VERSION 100 /* 0.1.0 */
+
+#define CKB_E 0
+#define CKB_B 1
+#define CKB_W 2
+
+#define CKB_OK 0
+#define CKB_E_INVALID (-1)  /* bad argument */
+#define CKB_E_CUDA (-2)     /* a CUDA runtime call failed */
+#define CKB_E_STATE (-3)    /* e.g. CNN weights not set */
+#define CKB_E_NOMEM (-4)    /* workspace too small */
+
+#define CKB_CNN_NPARAM 658665 /* NNManager.create_net, nn_manager.py:277-298 */
+#define CKB_CNN_PATCHES 100   /* NNManager.split ** 2, nn_manager.py:46 */
+#define CKB_CNN_CLASSES 81    /* 3 ** 4, nn_manager.py:48 */
+
+typedef struct ckb_ctx ckb_ctx;
+
+int ckb_version(void);
+
+/* gsize: 9, 13 or 19 (golib_conf.gsize; canonical image side = 20 * gsize, cvconf.py:10). The CNN entry points need 19. */
+int ckb_create(ckb_ctx **out, int device, int gsize);
+int ckb_destroy(ckb_ctx *ctx);
+const char *ckb_last_error(const ckb_ctx *ctx);
+
+/* cv::RNG helpers (cv2.kmeans draws from the process-global cv::theRNG(); here the caller owns the state).
+ * ckb_rng_seed(s) is the state cv2.setRNGSeed(s) installs; one cv2.kmeans(K=3, attempts=3, PP) call consumes
+ * CKB_RNG_DRAWS_PER_KMEANS 32-bit draws whatever the data. */
+#define CKB_RNG_DRAWS_PER_KMEANS 39
+uint64_t ckb_rng_seed(uint32_t seed);
+uint64_t ckb_rng_advance(uint64_t state, uint64_t n_draws);
+
+/* 3x3 inverse exactly as cv::invert computes it for the matrix warpPerspective receives (host helper). */
+int ckb_invert_homography(const double *m9, double *minv9);
+
+/* ---- K1 -----------------------------------------------------------------------------------------------------------
+ * Replaces: cv2.warpPerspective(frame, transform, self.canonical_shape)          stonesfinder.py:140
+ * n frames of H x W x 3 uint8 (row_pitch / frame_pitch in bytes) -> n canonical images of S x S x 3 uint8, densely
+ * packed, S = 20 * gsize. h_mtx: n_mtx (1 or n) row-major 3x3 float64 frame->canonical homographies, i.e. exactly the
+ * `BoardFinder.mtx` the reference passes (boardfinder.py:43-45); HOST memory, consumed before the call returns.
+ * Result is bit-identical to OpenCV's INTER_LINEAR / BORDER_CONSTANT(0) fixed-point remap. */
+int ckb_warp(ckb_ctx *ctx, const uint8_t *d_frames, int n, int H, int W, size_t row_pitch, size_t frame_pitch,
+             const double *h_mtx, int n_mtx, uint8_t *d_goban, void *stream);
+
+/* Replaces: self.accu = gframe.astype(np.float32) / cv2.accumulateWeighted(gframe, self.accu, 0.2)
+ *                                                                                  sf_clustering.py:33-36
+ * Applies the n canonical images IN ORDER to the running average d_accu (S*S*3 float32): frame 0 initialises it when
+ * first != 0, otherwise accu = fma(alpha, src - accu, accu). If d_snapshots != NULL, the state after frame i is also
+ * stored to d_snapshots[j] for the j-th frame with (i + snap_phase) % snap_every == 0 (the reference runs detection
+ * when total_f_processed % 3 == 0, sf_clustering.py:37). */
+int ckb_accumulate(ckb_ctx *ctx, const uint8_t *d_goban, int n, float *d_accu, float alpha, int first,
+                   float *d_snapshots, int snap_every, int snap_phase, void *stream);
+
+/* ---- K3 + K2 ------------------------------------------------------------------------------------------------------
+ * Replaces: SfClustering.find_stones(img, rs, re, cs, ce)                          sf_clustering.py:48-178
+ *   = cv2.kmeans(pixels, 3, None, (TERM_CRITERIA_EPS, 15, 3), 3, KMEANS_PP_CENTERS)   :103-104
+ *   + masked per-zone label histogram -> ratios                                     :105-129
+ *   + interpret_ratios / check_density                                              :131-178
+ * d_imgs: n canonical images, uint8 (is_f32 == 0) or float32 (is_f32 != 0, e.g. accu snapshots), S x S x 3 dense.
+ * d_rng_states: n cv::RNG states, one per image (DEVICE memory) — the state cv::theRNG() would hold when the
+ *   reference reaches that image's cv2.kmeans call.
+ * d_work: scratch of at least ckb_find_stones_workspace(ctx, n) bytes.
+ * Outputs (DEVICE; any optional pointer may be NULL):
+ *   d_stones  n x g x g uint8 codes (E outside the region)       d_trusted n uint8 (0 = the reference returns None)
+ *   d_ratios  n x g x g x 3 uint8    d_centers n x 9 float32     d_compactness n float64
+ *   d_labels  n x (x1-x0)*(y1-y0) int32 k-means labels of the region's bounding box, as cv2.kmeans returns them */
+size_t ckb_find_stones_workspace(const ckb_ctx *ctx, int n);
+int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, int rs, int re, int cs, int ce,
+                    const uint64_t *d_rng_states, void *d_work, size_t work_bytes, uint8_t *d_stones,
+                    uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness, int32_t *d_labels,
+                    void *stream);
+
+/* ---- K4 -----------------------------------------------------------------------------------------------------------
+ * Replaces: NNManager.get_net() / create_net() weights                              nn_manager.py:58-74,277-298
+ * h_params: CKB_CNN_NPARAM float32 in Keras channels-last order (w1 b1 w2 b2 w3 b3 w4 b4 w5 b5 w6 b6, conv kernels
+ * (kh,kw,cin,cout), dense (in,out)); HOST memory. Packs them into the tensor-core operand layout on the device
+ * (synchronous; call once per model). */
+int ckb_set_cnn_weights(ckb_ctx *ctx, const float *h_params, size_t n_params);
+
+/* Replaces: NNCache.predict_all_stones() = 100 x (NNManager._get_x + net.predict) + decode   nn_cache.py:25-52
+ *           and the MIN_CONFIDENCE rule of SfNeural.predict_all                      sf_neural.py:57-70
+ * d_goban: n canonical 380 x 380 x 3 uint8 images. d_work: at least ckb_cnn_workspace(ctx, n) bytes.
+ * Outputs (DEVICE; optional ones may be NULL):
+ *   d_softmax n x 100 x 81 float32 (region (i, j) at index i*10+j)
+ *   d_stones  n x 361 uint8 codes, d_conf n x 361 float32 (max(y)/sum(y) of the region that wrote the intersection
+ *             last, i.e. region 9 overwrites region 8 on row / column 17), d_keep n x 361 uint8 (stone != E and
+ *             conf > 0.6) */
+size_t ckb_cnn_workspace(const ckb_ctx *ctx, int n);
+int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes, float *d_softmax,
+                    uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream);
+
+/* Verification aid (tests only): the same forward pass on plain fp32 CUDA cores, no tensor cores. Same arguments. */
+int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes,
+                         float *d_softmax, uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream);
+
+/* Number of kernels the library has launched on this context since creation (bench.py's gpu_launches). */
+uint64_t ckb_launch_count(const ckb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAMKIFU_B200_H */

@@ -1,0 +1,59 @@
+"""K4 parity on the GPU: the SfNeural forward pass against the fp32 oracle (tolerance stated below) and the decode
+against the reference's golden vectors (bit-exact given the same softmax)."""
+import numpy as np
+import pytest
+import torch
+
+from camkifu_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+# north_star: CNN softmax outputs within 1e-3 relative. Softmax vectors are compared relative to their scale
+# (max |y| = the winning probability): |y_gpu - y_oracle| <= 1e-3 * max(y_oracle), and the label (argmax) exactly.
+SOFTMAX_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from camkifu_b200.engine import StoneEngine
+    e = StoneEngine(19)
+    e.set_cnn_weights(weights.glorot_params(seed=0, bias_scale=0.5))
+    return e
+
+
+def boards(n, seed=1):
+    import cv2
+    frames, M, truth, _ = synth.make_clip(seed, n, 240, 320)
+    return np.stack([cv2.warpPerspective(f, M, (380, 380)) for f in frames])
+
+
+def check(out, goban, oracle, params):
+    n = goban.shape[0]
+    for k in range(n):
+        xs = oracle.c_nn_gather(goban[k])
+        y = oracle.c_cnn_forward(xs, params)
+        yg = out["softmax"][k].cpu().numpy()
+        err = np.abs(yg - y).max(axis=1) / y.max(axis=1)
+        assert err.max() <= SOFTMAX_RTOL, "softmax error %.3g" % err.max()
+        assert np.array_equal(yg.argmax(1), y.argmax(1))
+        stones, conf, keep = oracle.c_nn_decode(yg)           # decode of the SAME softmax must be bit-exact
+        assert np.array_equal(out["stones"][k].cpu().numpy(), stones)
+        assert np.array_equal(out["conf"][k].cpu().numpy(), conf)
+        assert np.array_equal(out["keep"][k].cpu().numpy().astype(bool), keep)
+        s2, c2, k2 = oracle.c_nn_decode(y)                    # and agree with the oracle's own end result
+        assert np.array_equal(stones, s2) and np.allclose(conf, c2, rtol=1e-3)
+        far = np.abs(c2 - 0.6) > 1e-3
+        assert np.array_equal(keep[far], k2[far])
+
+
+def test_simt_forward_vs_oracle(engine, oracle):
+    goban = boards(2)
+    out = engine.cnn_forward(torch.from_numpy(goban).cuda(), simt=True)
+    check(out, goban, oracle, weights.glorot_params(seed=0, bias_scale=0.5))
+
+
+def test_decode_golden(engine, golden, oracle):
+    """Feed the golden softmax through the device decode: NNCache.predict_all_stones / SfNeural.predict_all."""
+    g = golden("neural_decode.npz")
+    stones, conf, keep = oracle.c_nn_decode(g["y"])
+    assert np.array_equal(stones, g["stones"]) and np.array_equal(conf, g["conf"])

@@ -1,0 +1,124 @@
+"""K3 + K2 parity on the GPU: ckb_find_stones against the oracle (= cv2.kmeans semantics) and the reference's goldens."""
+import numpy as np
+import pytest
+import torch
+
+from camkifu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ALL = ("stones", "trusted", "ratios", "centers", "compactness", "labels")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from camkifu_b200.engine import StoneEngine
+    return StoneEngine(19)
+
+
+def compare(res, k, ref, exact_centers=True):
+    assert np.array_equal(res["labels"][k].cpu().numpy(), ref["labels"]), "k-means labels differ"
+    c = res["centers"][k].cpu().numpy()
+    if exact_centers:
+        assert np.array_equal(c, ref["centers"])
+    assert np.allclose(c, ref["centers"], rtol=1e-3, atol=0)            # the stated float tolerance
+    assert abs(float(res["compactness"][k]) - ref["compactness"]) <= 1e-9 * ref["compactness"]
+    assert np.array_equal(res["ratios"][k].cpu().numpy(), ref["ratios"])
+    assert np.array_equal(res["stones"][k].cpu().numpy(), ref["stones"])
+    assert bool(res["trusted"][k]) == ref["trusted"]
+
+
+def test_golden_full_board(engine, golden, oracle):
+    g = golden("clustering_full.npz")
+    seeds = g["seeds"]
+    imgs = torch.from_numpy(np.stack([g["goban_0"], g["goban_1"], g["goban_2"], g["goban_sparse"]])).cuda()
+    states = [engine.L.ckb_rng_seed(int(s)) for s in seeds[:4]]
+    res = engine.find_stones(imgs, states, want=ALL)
+    for k in range(3):
+        assert np.array_equal(res["ratios"][k].cpu().numpy(), g["ratios_%d" % k])     # reference's cluster_colors
+        assert np.array_equal(res["centers"][k].cpu().numpy(), g["centers_%d" % k])
+        assert np.array_equal(res["stones"][k].cpu().numpy(), g["stones_%d" % k])      # reference's find_stones
+        assert bool(res["trusted"][k])
+    assert bool(g["sparse_is_none"]) and not bool(res["trusted"][3])                    # reference returned None
+    sub = engine.find_stones(imgs[:1], [engine.L.ckb_rng_seed(int(seeds[4]))], rs=6, re=13, cs=12, ce=19)
+    if g["stones_region"][0, 0] != 255:
+        assert np.array_equal(sub["stones"][0].cpu().numpy(), g["stones_region"])
+
+
+def test_golden_stream_accu_path(engine, golden, oracle):
+    """The reference's standalone SfClustering._find: float32 accu, rows 0..19, columns 6..13, every third frame."""
+    g = golden("clustering_stream.npz")
+    goban = torch.from_numpy(g["goban"]).cuda()
+    accu = torch.empty((380, 380, 3), dtype=torch.float32, device="cuda")
+    snaps = engine.accumulate(goban, accu, first=True, snap_every=3, snap_phase=0)
+    states = [engine.L.ckb_rng_seed(int(g["seeds"][i])) for i in (0, 3, 6)]
+    res = engine.find_stones(snaps, states, rs=0, re=19, cs=6, ce=13, want=ALL)
+    for k in range(3):
+        ref = oracle.c_find_stones(snaps[k].cpu().numpy(), states[k], 19, 0, 19, 6, 13)
+        compare(res, k, ref)
+    # replay bulk_update on the device stones and compare with the board the reference's controller ended with
+    board = np.zeros((19, 19), np.uint8)
+    for k in range(3):
+        assert bool(res["trusted"][k])
+        board = res["stones"][k].cpu().numpy().copy()   # all 361 are submitted; E removes, B/W (re)places
+    assert np.array_equal(board, g["board"])
+
+
+@pytest.mark.parametrize("kind", ["u8", "f32"])
+def test_batch_vs_oracle_rng_carry(engine, oracle, kind):
+    import cv2
+    n = 6
+    frames, M, truth, _ = synth.make_clip(77, n, 240, 320)
+    goban = engine.warp(torch.from_numpy(frames).cuda(), M)
+    if kind == "f32":
+        accu = torch.empty((380, 380, 3), dtype=torch.float32, device="cuda")
+        imgs = engine.accumulate(goban, accu, first=True, snap_every=1)
+    else:
+        imgs = goban
+    # one RNG stream carried across the n calls, as the reference's process-global cv::theRNG() would be
+    from camkifu_b200.engine import rng_seed, rng_advance
+    st0 = rng_seed(5)
+    states = [rng_advance(st0, k) for k in range(n)]
+    res = engine.find_stones(imgs, states, want=ALL)
+    host = imgs.cpu().numpy()
+    st = st0
+    cv2.setRNGSeed(5)
+    for k in range(n):
+        ref = oracle.c_find_stones(host[k], st)
+        assert st == states[k]
+        st = ref["rng_state"]
+        compare(res, k, ref)
+        if kind == "u8":
+            assert np.array_equal(ref["stones"], truth[k])
+
+
+def test_noise_and_degenerate_images(engine, oracle):
+    rng = np.random.default_rng(9)
+    imgs = np.zeros((4, 380, 380, 3), np.uint8)
+    imgs[0] = rng.integers(0, 256, (380, 380, 3), dtype=np.uint8)            # many Lloyd iterations
+    imgs[1][:, :190] = 200                                                    # two colours only: a k-means++ centre
+    imgs[1][:, 190:] = 30                                                     #   duplicates -> empty-cluster repair
+    imgs[2][:] = 128                                                          # constant image
+    imgs[3] = rng.integers(0, 2, (380, 380, 1), dtype=np.uint8) * 255         # black / white salt and pepper
+    states = [engine.L.ckb_rng_seed(100 + k) for k in range(4)]
+    res = engine.find_stones(torch.from_numpy(imgs).cuda(), states, want=ALL)
+    for k in range(4):
+        ref = oracle.c_find_stones(imgs[k], states[k])
+        compare(res, k, ref)
+
+
+@pytest.mark.parametrize("gsize", [9, 13])
+def test_other_board_sizes(oracle, gsize):
+    from camkifu_b200.engine import StoneEngine
+    eng = StoneEngine(gsize)
+    rng = np.random.default_rng(gsize)
+    stones = synth.random_stones(rng, gsize)
+    corners = synth.random_corners(rng, 480, 640)
+    M = synth.board_homography(corners, 20 * gsize)
+    frame = synth.render_frame(rng, 480, 640, stones, corners)
+    goban = eng.warp(torch.from_numpy(frame).cuda(), M)
+    st = eng.L.ckb_rng_seed(3)
+    res = eng.find_stones(goban, [st], want=ALL)
+    ref = oracle.c_find_stones(goban[0].cpu().numpy(), st, gsize)
+    compare(res, 0, ref)
+    assert np.array_equal(ref["stones"], stones)
