@@ -170,10 +170,25 @@ int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softm
     return CKB_OK;
 }
 
+// Tail of the tensor-core path (cnn_tc.cu): fc2 (160 -> 81, 13 k MAC per patch, float32 FMA) + softmax + decode.
+// d_tmp: n*100*(81 + 81 + 2) floats.
+int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, float *d_softmax, uint8_t *d_stones,
+                          float *d_conf, uint8_t *d_keep, cudaStream_t st)
+{
+    const int P = n * 100;
+    const float *w = ctx->cnn->d_params;
+    float *logits = (float *)d_tmp;
+    cnn_dense_simt<160, 81, false><<<(unsigned)(((long long)P * CNN_F6 + 255) / 256), 256, 0, st>>>(d_f5, w + OFF_W6, w + OFF_B6, logits, P);
+    CKB_LAUNCH_CHECK(ctx, "cnn_fc2");
+    return ckb_launch_decode(ctx, logits, n, d_softmax, logits + (size_t)P * CNN_F6, d_stones, d_conf, d_keep, st);
+}
+
 // workspace of the SIMT path, floats per patch
 #define SIMT_PER_PATCH (CNN_A1 + CNN_A2 + CNN_P2 + CNN_A3 + CNN_A4 + CNN_P4 + CNN_F5 + CNN_F6 + CNN_F6 + 2)
 
 size_t ckb_cnn_simt_workspace(int n) { return (size_t)n * 100 * SIMT_PER_PATCH * sizeof(float) + 256; }
+
+extern "C" size_t ckb_cnn_workspace_simt(const ckb_ctx *ctx, int n) { return (!ctx || n < 0) ? 0 : ckb_cnn_simt_workspace(n); }
 
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 

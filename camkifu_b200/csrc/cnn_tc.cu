@@ -1,11 +1,608 @@
-// K4 — tensor-core (tcgen05) forward pass of the SfNeural CNN.  (placeholder: filled in next)
+// K4 — forward pass of the SfNeural CNN on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces NNCache.predict_all_stones = 100 x (NNManager._get_x + net.predict) (src/camkifu/stone/nn_cache.py:25-52)
+// for the network of NNManager.create_net (nn_manager.py:277-298).
+//
+// Formulation. Every layer is a "shifted GEMM" over a flat list of pixels. Activations live in HBM as channel-chunk
+// planes [plane hi|lo][chunk of 8 channels][pixel][8 x bf16]: a pixel's 8 channels are one 16-byte unit, and consecutive
+// pixels of a plane are consecutive units — exactly the un-swizzled K-major core-matrix layout of the tcgen05 shared
+// memory descriptors (8 rows x 16 bytes contiguous, SBO = 128 B between row groups, LBO = plane stride between the two
+// K chunks). A 128-pixel tile plus its halo is therefore staged with one 1-D bulk copy (TMA, cp.async.bulk) per plane,
+// and the A operand of filter tap (dy, dx) is the SAME shared-memory tile with its descriptor start address advanced
+// by (dy * row_width + dx) pixels: implicit GEMM without im2col and without any shared-memory re-layout. Outputs are
+// computed for every pixel of the input grid; the epilogue keeps the valid ones and compacts them into the next
+// layer's grid. The dense layer fc1 runs through the same kernel with the 36 pooled pixels as "taps" whose A tiles
+// are streamed next to their weights.
+//
+// Precision. Inputs are raw 0..255 and the parity bar on the softmax is 1e-3 relative, which single-pass bf16 or tf32
+// operands miss by 1-2 orders of magnitude. Each float32 operand is therefore split into bf16 hi + lo
+// and three tensor-core products are accumulated in float32:  A_hi W_hi + A_hi W_lo + A_lo W_hi  (the uint8 network
+// input is exact in bf16, so conv1 needs two). Narrow layers (N = 32) put W_hi | W_lo side by side in the B operand so
+// that A_hi is read from shared memory once for both (the MMA is shared-memory bound at N = 32).
+//
+// Kernel structure (one persistent CTA per SM, 192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (single thread), warps 2-5 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
+// mbarrier pipelines: A tile full/empty (double buffered), weight/A stage ring full/empty, accumulator full/empty
+// (two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cuda_bf16.h>
+
+#include <new>
+
 #include "cnn_common.cuh"
 
 size_t ckb_cnn_simt_workspace(int n);
+int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, float *d_softmax, uint8_t *d_stones,
+                          float *d_conf, uint8_t *d_keep, cudaStream_t st);
 
-int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *h_params)
+// ------------------------------------------------------------------------------------------------------ layer configs
+struct Conv1Cfg {   // input: 16-channel "row window" expansion of the patch (k = dx*3 + c), taps = dy
+    static constexpr int NTAPS = 5, GW = 40, HW_IN = 1600, OH = 36, OW = 36, KC = 2, N = 32, A_PLANES = 1;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr int KCS = 2, NSTAGE = 1;
+    __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
+};
+struct Conv2Cfg {
+    static constexpr int NTAPS = 25, GW = 36, HW_IN = 1296, OH = 32, OW = 32, KC = 4, N = 32, A_PLANES = 2;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr int KCS = 4, NSTAGE = 1;
+    __host__ __device__ static constexpr int tapoff(int t) { return (t / 5) * 36 + t % 5; }
+};
+struct Conv3Cfg {
+    static constexpr int NTAPS = 9, GW = 16, HW_IN = 256, OH = 14, OW = 14, KC = 4, N = 96, A_PLANES = 2;
+    static constexpr bool CONCAT = false, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr int KCS = 4, NSTAGE = 1;
+    __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 16 + t % 3; }
+};
+struct Conv4Cfg {
+    static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
+    static constexpr bool CONCAT = false, A_RES = true, W_RES = false, OUT_F32 = false;
+    static constexpr int KCS = 6, NSTAGE = 4;
+    __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
+};
+struct Fc1Cfg {     // "pixels" are patches; tap q = pooled pixel, its A tile is streamed with its weights
+    static constexpr int NTAPS = 36, GW = 1, HW_IN = 1, OH = 1, OW = 1, KC = 12, N = 160, A_PLANES = 2;
+    static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true;
+    static constexpr int KCS = 4, NSTAGE = 5;
+    __host__ __device__ static constexpr int tapoff(int) { return 0; }
+};
+
+template <class L>
+struct Derived {
+    static constexpr int HALO = L::A_RES ? L::tapoff(L::NTAPS - 1) : 0;
+    static constexpr int APLANE = ((128 + HALO) * 16 + 127) / 128 * 128;         // bytes of one A plane in smem
+    static constexpr int A_TILE = L::A_RES ? L::A_PLANES * L::KC * APLANE : 0;   // one resident A tile
+    static constexpr int NABUF = L::A_RES ? 2 : 0;
+    static constexpr int NB = 2 * L::N;                                          // B rows: W_hi | W_lo
+    static constexpr int W_TAP = L::KC * NB * 16;                                // bytes of one tap's weights
+    static constexpr int W_ALL = L::W_RES ? L::NTAPS * W_TAP : 0;
+    static constexpr int SPT = L::KC / L::KCS;                                   // stages per tap
+    static constexpr int W_STAGE = L::W_RES ? 0 : L::KCS * NB * 16;
+    static constexpr int A_STAGE = L::A_RES ? 0 : L::A_PLANES * L::KCS * 128 * 16;
+    static constexpr int STAGE = W_STAGE + A_STAGE;
+    static constexpr int NSTAGE = (L::W_RES && L::A_RES) ? 0 : L::NSTAGE;
+    static constexpr int ACC_COLS = L::CONCAT ? 2 * L::N : L::N;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
+                                     : 2 * ACC_COLS <= 256 ? 256 : 512;
+    static constexpr int SMEM = NABUF * A_TILE + W_ALL + NSTAGE * STAGE + 256 /*barriers*/ + 128 /*align*/;
+    static_assert(L::KC % L::KCS == 0 && L::KCS % 2 == 0, "stages hold whole K=16 steps");
+    static_assert(2 * ACC_COLS <= 512, "two accumulators must fit in TMEM");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(L::N % 16 == 0 && NB <= 512, "UMMA N constraints (M = 128)");
+};
+
+struct LayerArgs {
+    const uint4 *in;        // activation planes (bf16 x 8 units)
+    long long in_plane;     // plane stride in units (pixels)
+    const uint4 *w;         // packed weights [tap][chunk][row 0..2N)[8 bf16]
+    const float *bias;      // N floats (zero padded)
+    uint4 *out;             // next layer's planes [2][N/8][out_plane]
+    long long out_plane;
+    float *out_f32;         // OUT_F32: dense [pixel][N] instead
+    int n_tiles;            // 128-pixel tiles of the input grid
+    int n_patches;
+};
+
+// ------------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    (void)ctx; (void)h_params;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float *v)
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// un-swizzled K-major shared memory matrix descriptor: 8-row x 16-byte core matrices, rows 16 B apart,
+// SBO (next 8 rows) = 128 B, LBO (next 8 K elements) = lbo_bytes; descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
+{
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *(const uint32_t *)&v;
+}
+// x = hi + lo (+ O(2^-17 x)): hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// -------------------------------------------------------------------------------------------------- the layer kernel
+template <class L>
+__global__ void __launch_bounds__(192, 1) cnn_tc_layer(const __grid_constant__ LayerArgs args)
+{
+    using D = Derived<L>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *sA = smem;                                  // NABUF x A_TILE
+    uint8_t *sW = sA + D::NABUF * D::A_TILE;             // W_ALL
+    uint8_t *sS = sW + D::W_ALL;                         // NSTAGE x STAGE   (W part first, then A part)
+    uint64_t *bars = (uint64_t *)(sS + D::NSTAGE * D::STAGE);
+    // barrier map
+    const uint32_t b_afull = smem_u32(bars + 0);         // [2]
+    const uint32_t b_aempty = smem_u32(bars + 2);        // [2]
+    const uint32_t b_tfull = smem_u32(bars + 4);         // [2] accumulator ready
+    const uint32_t b_tempty = smem_u32(bars + 6);        // [2] accumulator drained
+    const uint32_t b_wfull = smem_u32(bars + 8);         // resident weights landed
+    const uint32_t b_sfull = smem_u32(bars + 9);         // [NSTAGE]
+    const uint32_t b_sempty = smem_u32(bars + 9 + 8);    // [NSTAGE]
+    uint32_t *tmem_slot = (uint32_t *)(bars + 26);
+    static_assert(D::NSTAGE <= 8, "barrier map");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = ((int)args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(b_afull + 8 * i, 1);
+            mbar_init(b_aempty + 8 * i, 1);
+            mbar_init(b_tfull + 8 * i, 1);
+            mbar_init(b_tempty + 8 * i, 4);
+        }
+        mbar_init(b_wfull, 1);
+        for (int i = 0; i < 8; i++) {
+            mbar_init(b_sfull + 8 * i, 1);
+            mbar_init(b_sempty + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)D::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================================================ producer: TMA bulk copies, one elected thread
+        if (lane == 0) {
+            if (L::W_RES) {
+                mbar_expect_tx(b_wfull, (uint32_t)D::W_ALL);
+                constexpr int PIECE = 32768;
+                for (int off = 0; off < D::W_ALL; off += PIECE)
+                    bulk_g2s(smem_u32(sW + off), (const uint8_t *)args.w + off,
+                             (uint32_t)(D::W_ALL - off < PIECE ? D::W_ALL - off : PIECE), b_wfull);
+            }
+            uint32_t sit = 0;  // stage counter
+            for (int i = 0; i < n_my; i++) {
+                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                if (L::A_RES) {
+                    const int ab = i & 1;
+                    mbar_wait(b_aempty + 8 * ab, ((i >> 1) & 1) ^ 1);
+                    mbar_expect_tx(b_afull + 8 * ab, (uint32_t)(L::A_PLANES * L::KC * (128 + D::HALO) * 16));
+                    for (int pl = 0; pl < L::A_PLANES * L::KC; pl++)
+                        bulk_g2s(smem_u32(sA + ab * D::A_TILE + pl * D::APLANE),
+                                 args.in + (long long)pl * args.in_plane + tile * 128, (128 + D::HALO) * 16,
+                                 b_afull + 8 * ab);
+                }
+                if constexpr (D::NSTAGE > 0) {
+                    for (int t = 0; t < L::NTAPS; t++)
+                        for (int g = 0; g < D::SPT; g++, sit++) {
+                            const int s = sit % D::NSTAGE;
+                            mbar_wait(b_sempty + 8 * s, ((sit / D::NSTAGE) & 1) ^ 1);
+                            mbar_expect_tx(b_sfull + 8 * s, (uint32_t)D::STAGE);
+                            uint8_t *dst = sS + s * D::STAGE;
+                            bulk_g2s(smem_u32(dst), (const uint8_t *)args.w + (size_t)t * D::W_TAP + (size_t)g * D::W_STAGE,
+                                     D::W_STAGE, b_sfull + 8 * s);
+                            if (!L::A_RES) {
+                                // A of tap t: planes [pl][t][chunk] of the input, 128 rows each
+                                for (int pl = 0; pl < L::A_PLANES; pl++)
+                                    for (int c = 0; c < L::KCS; c++)
+                                        bulk_g2s(smem_u32(dst + D::W_STAGE + (pl * L::KCS + c) * 2048),
+                                                 args.in + ((long long)(pl * L::NTAPS + t) * L::KC + g * L::KCS + c) *
+                                                               args.in_plane + tile * 128,
+                                                 2048, b_sfull + 8 * s);
+                            }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================================================== MMA issuer: one thread drives the tensor core
+        if (lane == 0) {
+            constexpr uint32_t IDESC_WIDE = umma_idesc(L::CONCAT ? 2 * L::N : L::N);
+            constexpr uint32_t IDESC_N = umma_idesc(L::N);
+            if (L::W_RES) mbar_wait(b_wfull, 0);
+            uint32_t sit = 0;
+            for (int i = 0; i < n_my; i++) {
+                const int acc = i & 1;
+                const uint32_t d_tmem = tmem_base + acc * D::ACC_COLS;
+                mbar_wait(b_tempty + 8 * acc, ((i >> 1) & 1) ^ 1);
+                const int ab = i & 1;
+                if (L::A_RES) mbar_wait(b_afull + 8 * ab, (i >> 1) & 1);
+                tc_fence_after();
+                uint32_t first = 1;
+                for (int t = 0; t < L::NTAPS; t++)
+                    for (int g = 0; g < D::SPT; g++) {
+                        uint32_t a_hi, a_lbo, a_lo_off, w_base;
+                        if constexpr (D::NSTAGE > 0) {
+                            const int s = sit % D::NSTAGE;
+                            mbar_wait(b_sfull + 8 * s, (sit / D::NSTAGE) & 1);
+                            tc_fence_after();
+                            w_base = smem_u32(sS + s * D::STAGE);
+                        } else {
+                            w_base = smem_u32(sW + t * D::W_TAP + g * L::KCS * D::NB * 16);
+                        }
+                        if (L::A_RES) {
+                            a_hi = smem_u32(sA + ab * D::A_TILE + g * L::KCS * D::APLANE) + L::tapoff(t) * 16;
+                            a_lbo = D::APLANE;
+                            a_lo_off = L::KC * D::APLANE;
+                        } else {
+                            a_hi = w_base + D::W_STAGE;
+                            a_lbo = 2048;
+                            a_lo_off = L::KCS * 2048;
+                        }
+#pragma unroll
+                        for (int k2 = 0; k2 < L::KCS / 2; k2++) {
+                            const uint64_t da = umma_desc(a_hi + 2 * k2 * a_lbo, a_lbo);
+                            const uint64_t db = umma_desc(w_base + 2 * k2 * D::NB * 16, D::NB * 16);
+                            if (L::CONCAT) {
+                                tc_mma_bf16(d_tmem, da, db, IDESC_WIDE, first ^ 1);           // A_hi [W_hi | W_lo]
+                                if (L::A_PLANES == 2)
+                                    tc_mma_bf16(d_tmem, umma_desc(a_hi + a_lo_off + 2 * k2 * a_lbo, a_lbo), db, IDESC_N, 1);
+                            } else {
+                                tc_mma_bf16(d_tmem, da, db, IDESC_N, first ^ 1);              // A_hi W_hi
+                                tc_mma_bf16(d_tmem, da, umma_desc(w_base + 2 * k2 * D::NB * 16 + L::N * 16, D::NB * 16),
+                                            IDESC_N, 1);                                       // A_hi W_lo
+                                if (L::A_PLANES == 2)
+                                    tc_mma_bf16(d_tmem, umma_desc(a_hi + a_lo_off + 2 * k2 * a_lbo, a_lbo), db, IDESC_N, 1);
+                            }
+                            first = 0;
+                        }
+                        if constexpr (D::NSTAGE > 0) {
+                            tc_commit(b_sempty + 8 * (sit % D::NSTAGE));   // stage reusable once these MMAs retire
+                            sit++;
+                        }
+                    }
+                if (L::A_RES) tc_commit(b_aempty + 8 * ab);
+                tc_commit(b_tfull + 8 * acc);
+            }
+        }
+    } else {
+        // ================================================= epilogue: TMEM -> registers -> bias / ReLU / split -> HBM
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        for (int i = 0; i < n_my; i++) {
+            const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+            const int acc = i & 1;
+            const long long p = tile * 128 + row;
+            const long long patch = p / L::HW_IN;
+            const int rem = (int)(p - patch * L::HW_IN);
+            const int y = rem / L::GW, x = rem - y * L::GW;
+            const bool valid = patch < args.n_patches && y < L::OH && x < L::OW;
+            const long long opix = patch * (L::OH * L::OW) + y * L::OW + x;
+            mbar_wait(b_tfull + 8 * acc, (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
+#pragma unroll 2
+            for (int j = 0; j < L::N / 8; j++) {
+                float v[8];
+                tc_ld8(taddr + 8 * j, v);
+                if (L::CONCAT) {
+                    float u[8];
+                    tc_ld8(taddr + L::N + 8 * j, u);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] += u[k];
+                } else {
+                    tc_ld_wait();
+                }
+                const float4 b0 = __ldg((const float4 *)args.bias + 2 * j), b1 = __ldg((const float4 *)args.bias + 2 * j + 1);
+                v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f);
+                v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
+                v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f);
+                v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
+                if (valid) {
+                    if (L::OUT_F32) {
+                        float4 *o = (float4 *)(args.out_f32 + opix * L::N + 8 * j);
+                        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+                        uint4 hi, lo;
+                        split8(v, hi, lo);
+                        args.out[(long long)j * args.out_plane + opix] = hi;
+                        args.out[(long long)(L::N / 8 + j) * args.out_plane + opix] = lo;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)D::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------- elementwise companions
+// conv1 input: per patch pixel the 16-channel row window k = dx*3 + c (dx < 5, c < 3; k = 15 and windows that leave the
+// patch are zero), uint8 -> bf16 (exact). Output planes [chunk 0|1][P*1600 (+pad)][8]. Reads the canonical image in
+// place (NNManager._get_x, nn_manager.py:216-225: 40x40 window at (40 i, 40 j), the last one shifted back to 340).
+__global__ void __launch_bounds__(256) cnn_tc_expand_input(const uint8_t *__restrict__ goban, int n_patches,
+                                                           uint4 *__restrict__ out, long long out_plane)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_patches * 1600) return;
+    const int patch = (int)(idx / 1600), rem = (int)(idx % 1600), py = rem / 40, px = rem % 40;
+    const int frame = patch / 100, r = patch % 100;
+    const int x0 = cnn_patch_origin(r / 10), y0 = cnn_patch_origin(r % 10);
+    const uint8_t *src = goban + ((size_t)frame * 380 * 380 + (size_t)(x0 + py) * 380 + y0 + px) * 3;
+    const int nb = min(15, (40 - px) * 3);   // bytes of the window that stay inside the patch row
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = k < nb ? (float)__ldg(src + k) : 0.f;
+    uint4 c0, c1;
+    c0.x = pack_bf16x2(v[0], v[1]); c0.y = pack_bf16x2(v[2], v[3]); c0.z = pack_bf16x2(v[4], v[5]); c0.w = pack_bf16x2(v[6], v[7]);
+    c1.x = pack_bf16x2(v[8], v[9]); c1.y = pack_bf16x2(v[10], v[11]); c1.z = pack_bf16x2(v[12], v[13]); c1.w = pack_bf16x2(v[14], v[15]);
+    out[idx] = c0;
+    out[out_plane + idx] = c1;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float *v)
+{
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+        v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+    }
+}
+
+// 2x2 max pooling of hi/lo planes. in: [2][KC][in_plane] on a W x W grid per patch; out pixel index is
+//   patch * (W/2)^2 + oy * (W/2) + ox          (TO_FC = false: next conv's grid)
+//   ((oy * (W/2) + ox) * KC + chunk) * out_plane + patch   (TO_FC = true: fc1's per-tap planes)
+template <int W, int KC, bool TO_FC>
+__global__ void __launch_bounds__(256) cnn_tc_pool(const uint4 *__restrict__ in, long long in_plane, int n_patches,
+                                                   uint4 *__restrict__ out, long long out_plane)
+{
+    constexpr int OW = W / 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_patches * OW * OW * KC;
+    if (idx >= total) return;
+    // TO_FC: patch fastest (coalesced writes of fc1's planes); otherwise output pixel fastest
+    int patch, oy, ox, c;
+    if (TO_FC) {
+        patch = (int)(idx % n_patches);
+        long long t = idx / n_patches;
+        c = (int)(t % KC); t /= KC;
+        ox = (int)(t % OW); oy = (int)(t / OW);
+    } else {
+        long long t = idx;
+        ox = (int)(t % OW); t /= OW;
+        oy = (int)(t % OW); t /= OW;
+        patch = (int)(t % n_patches);
+        c = (int)(t / n_patches);
+    }
+    const long long ip = (long long)patch * W * W + (2 * oy) * W + 2 * ox;
+    const uint4 *ph = in + (long long)c * in_plane + ip, *pl = in + (long long)(KC + c) * in_plane + ip;
+    float m[8], v[8];
+    unpack8(__ldg(ph), __ldg(pl), m);
+    unpack8(__ldg(ph + 1), __ldg(pl + 1), v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
+    unpack8(__ldg(ph + W), __ldg(pl + W), v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
+    unpack8(__ldg(ph + W + 1), __ldg(pl + W + 1), v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
+    uint4 hi, lo;
+    split8(m, hi, lo);
+    if (TO_FC) {
+        const int q = oy * OW + ox;
+        out[((long long)q * KC + c) * out_plane + patch] = hi;
+        out[((long long)(OW * OW + q) * KC + c) * out_plane + patch] = lo;
+    } else {
+        const long long op = (long long)patch * OW * OW + oy * OW + ox;
+        out[(long long)c * out_plane + op] = hi;
+        out[(long long)(KC + c) * out_plane + op] = lo;
+    }
+}
+
+// test aid: planes [2][KC][plane] -> dense float32 [pixel][C]
+__global__ void cnn_tc_unpack(const uint4 *__restrict__ in, long long in_plane, int KC, long long n_pix, int C,
+                              float *__restrict__ out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pix * KC) return;
+    const long long p = idx % n_pix;
+    const int c = (int)(idx / n_pix);
+    float v[8];
+    unpack8(in[(long long)c * in_plane + p], in[(long long)(KC + c) * in_plane + p], v);
+    for (int k = 0; k < 8; k++)
+        if (c * 8 + k < C) out[p * C + c * 8 + k] = v[k];
+}
+
+// ------------------------------------------------------------------------------------------------ host: weight packing
+static inline uint16_t bf16_rn(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);   // round to nearest even (parameters are finite, checked by the caller)
+    return (uint16_t)(u >> 16);
+}
+static inline float bf16_f(uint16_t h)
+{
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+struct TcBlob {
+    size_t off_w[5], off_b[5], total;
+};
+
+// packed device blob: per layer the bf16 operand planes [tap][chunk][row 0..2N)[8] followed by N padded float32 biases
+template <class L, class F>
+static void pack_layer(uint8_t *blob, size_t off_w, size_t off_b, F weight /*(tap, k, n) -> float*/, const float *bias,
+                       int n_real)
+{
+    uint16_t *w = (uint16_t *)(blob + off_w);
+    for (int t = 0; t < L::NTAPS; t++)
+        for (int c = 0; c < L::KC; c++)
+            for (int r = 0; r < 2 * L::N; r++)
+                for (int j = 0; j < 8; j++) {
+                    const int n = r % L::N;
+                    const float f = weight(t, c * 8 + j, n);
+                    const uint16_t hi = bf16_rn(f);
+                    const uint16_t v = r < L::N ? hi : bf16_rn(f - bf16_f(hi));
+                    w[(((size_t)t * L::KC + c) * 2 * L::N + r) * 8 + j] = v;
+                }
+    float *b = (float *)(blob + off_b);
+    for (int n = 0; n < L::N; n++) b[n] = n < n_real ? bias[n] : 0.f;
+}
+
+template <class L>
+static size_t layer_w_bytes() { return (size_t)L::NTAPS * L::KC * 2 * L::N * 16; }
+
+static TcBlob blob_layout()
+{
+    TcBlob b;
+    size_t o = 0;
+    const size_t wb[5] = {layer_w_bytes<Conv1Cfg>(), layer_w_bytes<Conv2Cfg>(), layer_w_bytes<Conv3Cfg>(),
+                          layer_w_bytes<Conv4Cfg>(), layer_w_bytes<Fc1Cfg>()};
+    const int nn[5] = {Conv1Cfg::N, Conv2Cfg::N, Conv3Cfg::N, Conv4Cfg::N, Fc1Cfg::N};
+    for (int i = 0; i < 5; i++) {
+        b.off_w[i] = o; o += (wb[i] + 255) / 256 * 256;
+        b.off_b[i] = o; o += ((size_t)nn[i] * 4 + 255) / 256 * 256;
+    }
+    b.total = o;
+    return b;
+}
+
+int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
+{
+    const TcBlob L = blob_layout();
+    uint8_t *h = new (std::nothrow) uint8_t[L.total];
+    if (!h) CKB_FAIL(ctx, CKB_E_NOMEM, "host allocation failed");
+    memset(h, 0, L.total);
+    const float *w1 = p + OFF_W1, *w2 = p + OFF_W2, *w3 = p + OFF_W3, *w4 = p + OFF_W4, *w5 = p + OFF_W5;
+    // conv1: tap = dy, k = dx*3 + c
+    pack_layer<Conv1Cfg>(h, L.off_w[0], L.off_b[0],
+                         [&](int t, int k, int n) { return k < 15 ? w1[((t * 5 + k / 3) * 3 + k % 3) * 32 + n] : 0.f; },
+                         p + OFF_B1, 32);
+    pack_layer<Conv2Cfg>(h, L.off_w[1], L.off_b[1], [&](int t, int k, int n) { return w2[(t * 32 + k) * 32 + n]; },
+                         p + OFF_B2, 32);
+    pack_layer<Conv3Cfg>(h, L.off_w[2], L.off_b[2],
+                         [&](int t, int k, int n) { return n < 90 ? w3[(t * 32 + k) * 90 + n] : 0.f; }, p + OFF_B3, 90);
+    pack_layer<Conv4Cfg>(h, L.off_w[3], L.off_b[3],
+                         [&](int t, int k, int n) { return (k < 90 && n < 90) ? w4[(t * 90 + k) * 90 + n] : 0.f; },
+                         p + OFF_B4, 90);
+    // fc1: tap = pooled pixel q = y*6 + x, k = channel; Keras Flatten is (H, W, C): feature = q*90 + c
+    pack_layer<Fc1Cfg>(h, L.off_w[4], L.off_b[4],
+                       [&](int t, int k, int n) { return k < 90 ? w5[((size_t)t * 90 + k) * 160 + n] : 0.f; },
+                       p + OFF_B5, 160);
+    cudaError_t e = cudaMalloc(&ctx->cnn->d_tc, L.total);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->cnn->d_tc, h, L.total, cudaMemcpyHostToDevice);
+    delete[] h;
+    if (e != cudaSuccess) CKB_FAIL(ctx, CKB_E_CUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(e));
+    ctx->cnn->tc_bytes = L.total;
+    // opt in to the large dynamic shared memory footprints once
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv1Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv2Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv2Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv3Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv3Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Fc1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Fc1Cfg>::SMEM));
     return CKB_OK;
 }
 
@@ -14,15 +611,143 @@ void ckb_cnn_tc_free(ckb_ctx *ctx)
     if (ctx->cnn && ctx->cnn->d_tc) { cudaFree(ctx->cnn->d_tc); ctx->cnn->d_tc = nullptr; }
 }
 
+// ---------------------------------------------------------------------------------------------------- workspace layout
+#define TC_MAX_FRAMES 64   // frames per internal pass (bounds the workspace: ~53 MB per frame)
+
+struct TcWork {
+    // plane strides in 16-byte units (pixels), each with a tail so that the last tile's halo read stays inside
+    long long x0_plane, a1_plane, a2_plane, p2_plane, a3_plane, a4_plane, p4_plane;
+    size_t x0, a1, a2, p2, a3, a4, p4, f5, tmp, total;
+};
+
+static long long plane_units(long long pixels, int halo) { return ((pixels + 127) / 128 * 128 + halo + 7) / 8 * 8; }
+
+static TcWork tc_work_layout(int nf)
+{
+    const long long P = (long long)nf * 100;
+    TcWork w;
+    w.x0_plane = plane_units(P * 1600, Derived<Conv1Cfg>::HALO);
+    w.a1_plane = plane_units(P * 1296, Derived<Conv2Cfg>::HALO);
+    w.a2_plane = plane_units(P * 1024, 0);
+    w.p2_plane = plane_units(P * 256, Derived<Conv3Cfg>::HALO);
+    w.a3_plane = plane_units(P * 196, Derived<Conv4Cfg>::HALO);
+    w.a4_plane = plane_units(P * 144, 0);
+    w.p4_plane = plane_units(P, 0);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
+    w.x0 = take((size_t)w.x0_plane * 16 * 2);
+    w.a1 = take((size_t)w.a1_plane * 16 * 8);
+    w.a2 = take((size_t)w.a2_plane * 16 * 8);
+    w.p2 = take((size_t)w.p2_plane * 16 * 8);
+    w.a3 = take((size_t)w.a3_plane * 16 * 24);
+    w.a4 = take((size_t)w.a4_plane * 16 * 24);
+    w.p4 = take((size_t)w.p4_plane * 16 * 2 * 36 * 12);
+    w.f5 = take((size_t)P * 160 * 4);
+    w.tmp = take((size_t)P * (81 + 81 + 2) * 4);
+    w.total = o;
+    return w;
+}
+
 extern "C" size_t ckb_cnn_workspace(const ckb_ctx *ctx, int n)
 {
     if (!ctx || n < 0) return 0;
-    return ckb_cnn_simt_workspace(n);
+    return tc_work_layout(n < TC_MAX_FRAMES ? n : TC_MAX_FRAMES).total + 256;
+}
+
+template <class L>
+static int launch_layer(ckb_ctx *ctx, const char *name, const void *in, long long in_plane, size_t off_w, size_t off_b,
+                        void *out, long long out_plane, float *out_f32, long long n_pixels, int n_patches, cudaStream_t st)
+{
+    LayerArgs a;
+    a.in = (const uint4 *)in;
+    a.in_plane = in_plane;
+    a.w = (const uint4 *)((const uint8_t *)ctx->cnn->d_tc + off_w);
+    a.bias = (const float *)((const uint8_t *)ctx->cnn->d_tc + off_b);
+    a.out = (uint4 *)out;
+    a.out_plane = out_plane;
+    a.out_f32 = out_f32;
+    a.n_tiles = (int)((n_pixels + 127) / 128);
+    a.n_patches = n_patches;
+    const int grid = a.n_tiles < ctx->num_sms ? a.n_tiles : ctx->num_sms;
+    cnn_tc_layer<L><<<grid, 192, Derived<L>::SMEM, st>>>(a);
+    CKB_LAUNCH_CHECK(ctx, name);
+    return CKB_OK;
+}
+
+#define TC_TRY(call)                 \
+    do {                             \
+        const int rc__ = (call);     \
+        if (rc__ != CKB_OK) return rc__; \
+    } while (0)
+
+static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t *work, float *d_softmax,
+                           uint8_t *d_stones, float *d_conf, uint8_t *d_keep, cudaStream_t st)
+{
+    const TcWork W = tc_work_layout(nf);
+    const TcBlob B = blob_layout();
+    const int P = nf * 100;
+    uint4 *x0 = (uint4 *)(work + W.x0), *a1 = (uint4 *)(work + W.a1), *a2 = (uint4 *)(work + W.a2);
+    uint4 *p2 = (uint4 *)(work + W.p2), *a3 = (uint4 *)(work + W.a3), *a4 = (uint4 *)(work + W.a4);
+    uint4 *p4 = (uint4 *)(work + W.p4);
+    float *f5 = (float *)(work + W.f5);
+    cnn_tc_expand_input<<<(unsigned)(((long long)P * 1600 + 255) / 256), 256, 0, st>>>(d_goban, P, x0, W.x0_plane);
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_expand_input");
+    TC_TRY(launch_layer<Conv1Cfg>(ctx, "cnn_tc_conv1", x0, W.x0_plane, B.off_w[0], B.off_b[0], a1, W.a1_plane, nullptr,
+                                  (long long)P * 1600, P, st));
+    TC_TRY(launch_layer<Conv2Cfg>(ctx, "cnn_tc_conv2", a1, W.a1_plane, B.off_w[1], B.off_b[1], a2, W.a2_plane, nullptr,
+                                  (long long)P * 1296, P, st));
+    cnn_tc_pool<32, 4, false><<<(unsigned)(((long long)P * 256 * 4 + 255) / 256), 256, 0, st>>>(a2, W.a2_plane, P, p2, W.p2_plane);
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool2");
+    TC_TRY(launch_layer<Conv3Cfg>(ctx, "cnn_tc_conv3", p2, W.p2_plane, B.off_w[2], B.off_b[2], a3, W.a3_plane, nullptr,
+                                  (long long)P * 256, P, st));
+    TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
+                                  (long long)P * 196, P, st));
+    cnn_tc_pool<12, 12, true><<<(unsigned)(((long long)P * 36 * 12 + 255) / 256), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool4");
+    TC_TRY(launch_layer<Fc1Cfg>(ctx, "cnn_tc_fc1", p4, W.p4_plane, B.off_w[4], B.off_b[4], nullptr, 0, f5, P, P, st));
+    return ckb_launch_fc2_decode(ctx, f5, nf, work + W.tmp, d_softmax, d_stones, d_conf, d_keep, st);
 }
 
 extern "C" int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes,
                                float *d_softmax, uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream)
 {
     if (!ctx) return CKB_E_INVALID;
-    CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_forward: tensor-core path not built yet");
+    if (!ctx->cnn || !ctx->cnn->d_tc) CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_forward: call ckb_set_cnn_weights first");
+    if (!d_goban || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward: bad argument");
+    if (work_bytes < ckb_cnn_workspace(ctx, n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_cnn_forward: workspace too small");
+    if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward: workspace must be 256-byte aligned");
+    if (n == 0) return CKB_OK;
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int f0 = 0; f0 < n; f0 += TC_MAX_FRAMES) {
+        const int nf = n - f0 < TC_MAX_FRAMES ? n - f0 : TC_MAX_FRAMES;
+        TC_TRY(tc_forward_pass(ctx, d_goban + (size_t)f0 * 380 * 380 * 3, nf, (uint8_t *)d_work,
+                               d_softmax ? d_softmax + (size_t)f0 * 100 * 81 : nullptr,
+                               d_stones ? d_stones + (size_t)f0 * 361 : nullptr, d_conf ? d_conf + (size_t)f0 * 361 : nullptr,
+                               d_keep ? d_keep + (size_t)f0 * 361 : nullptr, (cudaStream_t)stream));
+    }
+    return CKB_OK;
+}
+
+// Test aid: after ckb_cnn_forward on n <= 64 frames, unpack one intermediate activation of the tensor-core path from
+// the workspace into dense float32 [patch][H][W][C]: layer 1 = conv1 (36,36,32), 2 = pooled conv2 (16,16,32),
+// 3 = conv3 (14,14,90), 4 = pooled conv4 (6,6,90; from fc1's tap planes), 5 = fc1 (160).
+extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n, int layer, float *d_out, void *stream)
+{
+    if (!ctx || !d_work || !d_out || n < 1 || n > TC_MAX_FRAMES) return CKB_E_INVALID;
+    const TcWork W = tc_work_layout(n);
+    const uint8_t *work = (const uint8_t *)d_work;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = (long long)n * 100;
+    auto go = [&](size_t off, long long plane, int KC, long long npix, int C) {
+        cnn_tc_unpack<<<(unsigned)((npix * KC + 255) / 256), 256, 0, st>>>((const uint4 *)(work + off), plane, KC, npix, C, d_out);
+    };
+    switch (layer) {
+    case 1: go(W.a1, W.a1_plane, 4, P * 1296, 32); break;
+    case 2: go(W.p2, W.p2_plane, 4, P * 256, 32); break;
+    case 3: go(W.a3, W.a3_plane, 12, P * 196, 90); break;
+    case 5: CKB_CUDA(ctx, cudaMemcpyAsync(d_out, work + W.f5, (size_t)P * 160 * 4, cudaMemcpyDeviceToDevice, st)); return CKB_OK;
+    default: CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_debug_activation: layer must be 1, 2, 3 or 5");
+    }
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_unpack");
+    return CKB_OK;
 }

@@ -169,9 +169,17 @@ class StoneEngine:
                "keep": torch.empty((n, 19, 19), dtype=torch.uint8, device=dev)}
         if want_softmax:
             out["softmax"] = torch.empty((n, 100, 81), dtype=torch.float32, device=dev)
-        wb = self.L.ckb_cnn_workspace(self._h, n)
+        wb = (self.L.ckb_cnn_workspace_simt if simt else self.L.ckb_cnn_workspace)(self._h, n)
         work = self._workspace(wb)
         fn = self.L.ckb_cnn_forward_simt if simt else self.L.ckb_cnn_forward
         self._check(fn(self._h, self._ptr(goban), n, self._ptr(work), work.numel(), self._ptr(out.get("softmax")),
                        self._ptr(out["stones"]), self._ptr(out["conf"]), self._ptr(out["keep"]), self._stream()))
+        return out
+
+    def cnn_debug_activation(self, n: int, layer: int) -> torch.Tensor:
+        """Test aid: dense float32 copy of an intermediate activation of the last cnn_forward (n <= 64 frames)."""
+        shape = {1: (36, 36, 32), 2: (16, 16, 32), 3: (14, 14, 90), 5: (160,)}[layer]
+        out = torch.zeros((n * 100,) + shape, dtype=torch.float32, device=self.device)
+        self._check(self.L.ckb_cnn_debug_activation(self._h, self._ptr(self._work), n, layer, self._ptr(out),
+                                                    self._stream()))
         return out

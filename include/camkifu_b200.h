@@ -118,7 +118,13 @@ size_t ckb_cnn_workspace(const ckb_ctx *ctx, int n);
 int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes, float *d_softmax,
                     uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream);
 
-/* Verification aid (tests only): the same forward pass on plain fp32 CUDA cores, no tensor cores. Same arguments. */
+/* Verification aids (tests only). ckb_cnn_forward_simt: the same forward pass on plain fp32 CUDA cores, no tensor cores;
+ * same arguments, but d_work must hold ckb_cnn_workspace_simt(ctx, n) bytes. ckb_cnn_debug_activation: after
+ * ckb_cnn_forward on n <= 64 frames, unpacks one intermediate activation of the tensor-core path from its workspace into
+ * dense float32 [patch][H][W][C]: layer 1 = conv1 (36,36,32), 2 = pooled conv2 (16,16,32), 3 = conv3 (14,14,90),
+ * 5 = fc1 (160). */
+size_t ckb_cnn_workspace_simt(const ckb_ctx *ctx, int n);
+int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n, int layer, float *d_out, void *stream);
 int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes,
                          float *d_softmax, uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream);
 

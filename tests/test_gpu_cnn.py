@@ -57,3 +57,41 @@ def test_decode_golden(engine, golden, oracle):
     g = golden("neural_decode.npz")
     stones, conf, keep = oracle.c_nn_decode(g["y"])
     assert np.array_equal(stones, g["stones"]) and np.array_equal(conf, g["conf"])
+
+
+def test_tc_layers_vs_oracle(engine, oracle):
+    """Each tensor-core layer against the oracle's float32 activations (bf16 hi/lo split operands, 3 products):
+    relative to the layer's largest activation the error must stay below 1e-4."""
+    goban = boards(1, seed=5)
+    params = weights.glorot_params(seed=0, bias_scale=0.5)
+    engine.cnn_forward(torch.from_numpy(goban).cuda())
+    xs = oracle.c_nn_gather(goban[0])
+    y, acts = oracle.c_cnn_forward(xs, params, want_acts=True)
+    sizes = [("conv1", 1, 36 * 36 * 32), ("pool2", 2, 16 * 16 * 32), ("conv3", 3, 14 * 14 * 90), ("pool4", None, 3240),
+             ("fc1", 5, 160)]
+    off = 0
+    for name, layer, sz in sizes:
+        ref = acts[:, off:off + sz]
+        off += sz
+        if layer is None:
+            continue
+        got = engine.cnn_debug_activation(1, layer).cpu().numpy().reshape(100, -1)
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err < 1e-4, "%s: relative error %.3g" % (name, err)
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_tc_forward_vs_oracle(engine, oracle, n):
+    goban = boards(n, seed=2 + n)
+    out = engine.cnn_forward(torch.from_numpy(goban).cuda())
+    check(out, goban, oracle, weights.glorot_params(seed=0, bias_scale=0.5))
+
+
+def test_tc_matches_simt_on_noise(engine):
+    """Tensor-core path vs the fp32 CUDA-core path on white-noise images (largest activations, no structure)."""
+    rng = np.random.default_rng(11)
+    goban = torch.from_numpy(rng.integers(0, 256, (2, 380, 380, 3), dtype=np.uint8)).cuda()
+    a = engine.cnn_forward(goban)["softmax"].cpu().numpy()
+    b = engine.cnn_forward(goban, simt=True)["softmax"].cpu().numpy()
+    err = np.abs(a - b).max(axis=2) / b.max(axis=2)
+    assert err.max() <= SOFTMAX_RTOL, "softmax error %.3g" % err.max()
