@@ -1,5 +1,7 @@
 // C ABI of camkifu_b200 (see include/camkifu_b200.h): context management and argument validation; the kernels live in
 // warp.cu (K1), kmeans.cu (K3), zones.cu (K2), cnn_*.cu (K4).
+#include <math.h>
+
 #include <new>
 
 #include "ckb_common.cuh"
@@ -20,6 +22,108 @@ extern "C" uint64_t ckb_rng_advance(uint64_t state, uint64_t n_draws)
     // cv::RNG::next(): multiply-with-carry, state = (uint32)state * 4164903690 + (state >> 32)
     for (uint64_t i = 0; i < n_draws; i++) state = (uint64_t)(uint32_t)state * 4164903690ULL + (state >> 32);
     return state;
+}
+
+// ---- per-kernel timing -------------------------------------------------------------------------------------------
+void ckb_prof_mark(ckb_ctx *ctx, const char *name)
+{
+    if (ctx->prof_n >= ctx->prof_cap) return;  // full: later launches go untimed
+    ckb_prof_entry &e = ctx->prof[ctx->prof_n];
+    if (!e.ev && cudaEventCreate(&e.ev) != cudaSuccess) return;
+    e.name = name;
+    if (cudaEventRecord(e.ev, ctx->cur_stream) == cudaSuccess) ctx->prof_n++;
+}
+
+extern "C" int ckb_profile_begin(ckb_ctx *ctx, int capacity)
+{
+    if (!ctx || capacity < 2) return CKB_E_INVALID;
+    if (capacity > ctx->prof_cap) {
+        ckb_prof_entry *p = new (std::nothrow) ckb_prof_entry[capacity];
+        if (!p) CKB_FAIL(ctx, CKB_E_NOMEM, "host allocation failed");
+        memset(p, 0, sizeof(ckb_prof_entry) * capacity);
+        for (int i = 0; i < ctx->prof_cap; i++) p[i] = ctx->prof[i];
+        delete[] ctx->prof;
+        ctx->prof = p;
+        ctx->prof_cap = capacity;
+    }
+    ctx->prof_n = 0;
+    ctx->prof_on = 1;
+    return CKB_OK;
+}
+
+extern "C" int ckb_profile_end(ckb_ctx *ctx, int max_entries, char *names, float *ms, int *n_out)
+{
+    if (!ctx || !names || !ms || !n_out) return CKB_E_INVALID;
+    ctx->prof_on = 0;
+    *n_out = 0;
+    if (ctx->prof_n == 0) return CKB_OK;
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_CUDA(ctx, cudaEventSynchronize(ctx->prof[ctx->prof_n - 1].ev));
+    int k = 0;
+    for (int i = 1; i < ctx->prof_n && k < max_entries; i++) {
+        if (!ctx->prof[i].name) continue;
+        float t = 0.f;
+        CKB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof[i - 1].ev, ctx->prof[i].ev));
+        strncpy(names + (size_t)k * 32, ctx->prof[i].name, 31);
+        names[(size_t)k * 32 + 31] = 0;
+        ms[k++] = t;
+    }
+    *n_out = k;
+    return CKB_OK;
+}
+
+// ---- host -> device staging of the part of each frame the warp can touch --------------------------------------------
+extern "C" int ckb_frame_roi(const double *m9, int H, int W, int S, int *roi4)
+{
+    // The canonical square [0, S-1]^2 maps (through the inverse homography) inside the convex hull of its four corner
+    // images; bilinear taps reach one pixel further right / down. roi = {y0, y1, x0, x1}, half-open, clipped.
+    if (!m9 || !roi4 || H < 1 || W < 1 || S < 1) return CKB_E_INVALID;
+    double inv[9];
+    if (ckb_invert_homography(m9, inv) != CKB_OK) { roi4[0] = 0; roi4[1] = H; roi4[2] = 0; roi4[3] = W; return CKB_OK; }
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    bool ok = true;
+    double wsign = 0;
+    for (int c = 0; c < 4; c++) {
+        const double x = (c & 1) ? S - 1 : 0, y = (c & 2) ? S - 1 : 0;
+        const double w = inv[6] * x + inv[7] * y + inv[8];
+        if (w == 0 || (wsign != 0 && (w > 0) != (wsign > 0))) ok = false;   // horizon crosses the board: no bound
+        wsign = w;
+        const double sx = (inv[0] * x + inv[1] * y + inv[2]) / w, sy = (inv[3] * x + inv[4] * y + inv[5]) / w;
+        xmin = sx < xmin ? sx : xmin; xmax = sx > xmax ? sx : xmax;
+        ymin = sy < ymin ? sy : ymin; ymax = sy > ymax ? sy : ymax;
+    }
+    if (!ok || !(xmin == xmin) || !(ymin == ymin)) { roi4[0] = 0; roi4[1] = H; roi4[2] = 0; roi4[3] = W; return CKB_OK; }
+    auto clampi = [](double v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : (int)v); };
+    roi4[0] = clampi(floor(ymin) - 1, 0, H);
+    roi4[1] = clampi(ceil(ymax) + 3, 0, H);
+    roi4[2] = clampi(floor(xmin) - 1, 0, W);
+    roi4[3] = clampi(ceil(xmax) + 3, 0, W);
+    if (roi4[1] <= roi4[0] || roi4[3] <= roi4[2]) { roi4[0] = roi4[1] = roi4[2] = roi4[3] = 0; }
+    return CKB_OK;
+}
+
+extern "C" int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, int H, int W, size_t h_row_pitch,
+                                 size_t h_frame_pitch, const int *roi4, uint8_t *d_frames, size_t d_row_pitch,
+                                 size_t d_frame_pitch, void *stream)
+{
+    if (!ctx) return CKB_E_INVALID;
+    if (!h_frames || !d_frames || n < 0 || H < 1 || W < 1) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: bad argument");
+    int y0 = 0, y1 = H, x0 = 0, x1 = W;
+    if (roi4) { y0 = roi4[0]; y1 = roi4[1]; x0 = roi4[2]; x1 = roi4[3]; }
+    if (y0 < 0 || x0 < 0 || y1 > H || x1 > W) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: roi outside the frame");
+    if (y1 <= y0 || x1 <= x0 || n == 0) return CKB_OK;
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t wbytes = (size_t)(x1 - x0) * 3;
+    for (int i = 0; i < n; i++) {
+        const uint8_t *src = h_frames + (size_t)i * h_frame_pitch + (size_t)y0 * h_row_pitch + (size_t)x0 * 3;
+        uint8_t *dst = d_frames + (size_t)i * d_frame_pitch + (size_t)y0 * d_row_pitch + (size_t)x0 * 3;
+        if (wbytes == h_row_pitch && wbytes == d_row_pitch)
+            CKB_CUDA(ctx, cudaMemcpyAsync(dst, src, wbytes * (size_t)(y1 - y0), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        else
+            CKB_CUDA(ctx, cudaMemcpy2DAsync(dst, d_row_pitch, src, h_row_pitch, wbytes, (size_t)(y1 - y0),
+                                            cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
+    return CKB_OK;
 }
 
 extern "C" int ckb_invert_homography(const double *m, double *t)
@@ -87,6 +191,9 @@ extern "C" int ckb_destroy(ckb_ctx *ctx)
     ckb_cnn_free(ctx);
     if (ctx->d_rects) cudaFree(ctx->d_rects);
     if (ctx->d_mask) cudaFree(ctx->d_mask);
+    for (int i = 0; i < ctx->prof_cap; i++)
+        if (ctx->prof[i].ev) cudaEventDestroy(ctx->prof[i].ev);
+    delete[] ctx->prof;
     delete ctx;
     return CKB_OK;
 }
@@ -102,6 +209,7 @@ extern "C" int ckb_warp(ckb_ctx *ctx, const uint8_t *d_frames, int n, int H, int
     if (H > 32767 || W > 32767) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_warp: frames larger than 32767 are not supported (as OpenCV)");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
     // invert on the host exactly as OpenCV does; a singular matrix yields the zero matrix (every tap at (0,0))
     double *minv = new (std::nothrow) double[(size_t)n_mtx * 9];
     if (!minv) CKB_FAIL(ctx, CKB_E_NOMEM, "host allocation failed");
@@ -118,6 +226,7 @@ extern "C" int ckb_accumulate(ckb_ctx *ctx, const uint8_t *d_goban, int n, float
     if (!d_goban || !d_accu || n < 0 || snap_phase < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_accumulate: bad argument");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
     return ckb_launch_accumulate(ctx, d_goban, n, d_accu, alpha, first, d_snapshots, snap_every, snap_phase,
                                  (cudaStream_t)stream);
 }

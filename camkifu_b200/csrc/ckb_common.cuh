@@ -13,6 +13,11 @@
 
 struct ckb_cnn_weights;  // cnn_pack.cu
 
+struct ckb_prof_entry {
+    const char *name;   // NULL = boundary marker (entry of an API call)
+    cudaEvent_t ev;
+};
+
 struct ckb_ctx {
     int device;
     int gsize;
@@ -25,7 +30,20 @@ struct ckb_ctx {
     uint8_t *d_mask;    // [S*S] disk mask
     int32_t h_rects[CKB_MAX_ZONES * 4];
     ckb_cnn_weights *cnn;
+    // per-kernel timing (ckb_profile_begin / ckb_profile_end): one CUDA event after every launch on the caller's stream
+    cudaStream_t cur_stream;
+    int prof_on, prof_n, prof_cap;
+    ckb_prof_entry *prof;
 };
+
+void ckb_prof_mark(ckb_ctx *ctx, const char *name);
+
+// every kernel-launching entry point starts with this: remembers the stream and opens a timing interval
+#define CKB_ENTER(ctx, st)                             \
+    do {                                               \
+        (ctx)->cur_stream = (cudaStream_t)(st);        \
+        if ((ctx)->prof_on) ckb_prof_mark(ctx, nullptr); \
+    } while (0)
 
 #define CKB_FAIL(ctx, code, ...)                              \
     do {                                                      \
@@ -45,6 +63,7 @@ struct ckb_ctx {
         cudaError_t e__ = cudaGetLastError();                                                             \
         if (e__ != cudaSuccess) CKB_FAIL(ctx, CKB_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
         (ctx)->launches++;                                                                                \
+        if ((ctx)->prof_on) ckb_prof_mark(ctx, name);                                                     \
     } while (0)
 
 // geometry (host side, geometry.cu)

@@ -201,6 +201,7 @@ extern "C" int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n,
     if (work_bytes < ckb_cnn_simt_workspace(n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_cnn_forward_simt: workspace too small");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int P = n * 100;
     const float *w = ctx->cnn->d_params;

@@ -718,6 +718,7 @@ extern "C" int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void
     if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward: workspace must be 256-byte aligned");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
     for (int f0 = 0; f0 < n; f0 += TC_MAX_FRAMES) {
         const int nf = n - f0 < TC_MAX_FRAMES ? n - f0 : TC_MAX_FRAMES;
         TC_TRY(tc_forward_pass(ctx, d_goban + (size_t)f0 * 380 * 380 * 3, nf, (uint8_t *)d_work,
@@ -737,6 +738,7 @@ extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n,
     const TcWork W = tc_work_layout(n);
     const uint8_t *work = (const uint8_t *)d_work;
     cudaStream_t st = (cudaStream_t)stream;
+    CKB_ENTER(ctx, stream);
     const long long P = (long long)n * 100;
     auto go = [&](size_t off, long long plane, int KC, long long npix, int C) {
         cnn_tc_unpack<<<(unsigned)((npix * KC + 255) / 256), 256, 0, st>>>((const uint4 *)(work + off), plane, KC, npix, C, d_out);

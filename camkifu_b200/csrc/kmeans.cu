@@ -633,6 +633,7 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
     if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: workspace must be 256-byte aligned");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const Region rg = make_region(ctx, rs, re, cs, ce);
     const size_t stride = align_up((size_t)ctx->S * ctx->S * 16, 256);

@@ -183,3 +183,43 @@ class StoneEngine:
         self._check(self.L.ckb_cnn_debug_activation(self._h, self._ptr(self._work), n, layer, self._ptr(out),
                                                     self._stream()))
         return out
+
+    # ------------------------------------------------------------------------------------------------ host staging
+    def frame_roi(self, mtx, H: int, W: int):
+        """(y0, y1, x0, x1): the part of an H x W frame the warp can read under homography mtx."""
+        m = np.ascontiguousarray(np.asarray(mtx, dtype=np.float64)).reshape(9)
+        roi = np.zeros(4, np.int32)
+        rc = self.L.ckb_frame_roi(m.ctypes.data_as(C.c_void_p), H, W, self.S, roi.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise CkbError(rc, "ckb_frame_roi: bad argument")
+        return tuple(int(v) for v in roi)
+
+    def upload_frames(self, host: torch.Tensor, dev: torch.Tensor, roi=None):
+        """Asynchronous H2D copy (current stream) of `roi` of each HOST frame [n, H, W, 3] into dev [>= n, H, W, 3]."""
+        assert not host.is_cuda and dev.is_cuda and host.dtype == torch.uint8 and dev.dtype == torch.uint8
+        assert host.dim() == 4 and host.stride(3) == 1 and host.stride(2) == 3 and dev.stride(2) == 3
+        n, H, W, _ = host.shape
+        assert dev.shape[0] >= n and tuple(dev.shape[1:]) == (H, W, 3)
+        r = None
+        if roi is not None:
+            r = np.asarray(roi, dtype=np.int32)
+        self._check(self.L.ckb_upload_frames(self._h, C.c_void_p(host.data_ptr()), n, H, W, host.stride(1),
+                                             host.stride(0), r.ctypes.data_as(C.c_void_p) if r is not None else None,
+                                             self._ptr(dev), dev.stride(1), dev.stride(0), self._stream()))
+        bytes_per_frame = (H * W * 3) if roi is None else (roi[1] - roi[0]) * (roi[3] - roi[2]) * 3
+        return n * bytes_per_frame
+
+    # ------------------------------------------------------------------------------------------- per-kernel timing
+    def profile_begin(self, capacity: int = 8192):
+        self._check(self.L.ckb_profile_begin(self._h, capacity))
+        self._prof_cap = capacity
+
+    def profile_end(self):
+        """[(kernel name, ms)] for every launch since profile_begin, in issue order."""
+        cap = getattr(self, "_prof_cap", 8192)
+        names = C.create_string_buffer(cap * 32)
+        ms = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        self._check(self.L.ckb_profile_end(self._h, cap, names, ms.ctypes.data_as(C.c_void_p), C.byref(n)))
+        raw = names.raw
+        return [(raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]

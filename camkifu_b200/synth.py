@@ -107,3 +107,28 @@ def make_clip(seed: int, n: int, H: int, W: int, gsize: int = 19, new_board_ever
         frames[i] = render_frame(rng, H, W, stones, corners, background=bg)
         truth[i] = stones
     return frames, mtx, truth, corners
+
+
+def make_clip_parallel(seed: int, n: int, H: int, W: int, gsize: int = 19, workers: int = 0):
+    """Same kind of clip as make_clip (fixed corners and background, a new random position every frame), rendered by a
+    thread pool with one child generator per frame. Returns (frames, mtx, truth, corners)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    root = np.random.SeedSequence(seed)
+    rng0 = np.random.default_rng(root.spawn(1)[0])
+    corners = random_corners(rng0, H, W)
+    mtx = board_homography(corners, 20 * gsize)
+    bg = make_background(rng0, H, W)
+    frames = np.empty((n, H, W, 3), dtype=np.uint8)
+    truth = np.empty((n, gsize, gsize), dtype=np.uint8)
+    children = root.spawn(n + 1)[1:]
+
+    def one(i):
+        rng = np.random.default_rng(children[i])
+        stones = random_stones(rng, gsize)
+        frames[i] = render_frame(rng, H, W, stones, corners, background=bg)
+        truth[i] = stones
+
+    with ThreadPoolExecutor(max_workers=workers or min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(n)))
+    return frames, mtx, truth, corners

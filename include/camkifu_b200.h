@@ -128,6 +128,24 @@ int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n, int layer,
 int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, size_t work_bytes,
                          float *d_softmax, uint8_t *d_stones, float *d_conf, uint8_t *d_keep, void *stream);
 
+/* ---- host <-> device staging ----------------------------------------------------------------------------------------
+ * ckb_frame_roi: the part of an H x W frame that ckb_warp can read for homography m9 (frame -> canonical S x S):
+ * roi4 = {y0, y1, x0, x1}, half-open (host helper; the whole frame when the homography gives no bound).
+ * ckb_upload_frames: asynchronous copy of that region of n HOST frames (pinned memory for real overlap) into the device
+ * frame buffer ckb_warp reads; roi4 == NULL copies whole frames. Replaces nothing in the reference (which has no
+ * device); it is the H2D leg of StonesFinder._doframe's `frame` argument (stonesfinder.py:123). */
+int ckb_frame_roi(const double *m9, int H, int W, int S, int *roi4);
+int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, int H, int W, size_t h_row_pitch,
+                      size_t h_frame_pitch, const int *roi4, uint8_t *d_frames, size_t d_row_pitch,
+                      size_t d_frame_pitch, void *stream);
+
+/* ---- per-kernel timing (bench.py's roofline) ---------------------------------------------------------------------------
+ * Between ckb_profile_begin and ckb_profile_end the library records a CUDA event on the caller's stream after every
+ * kernel it launches (up to `capacity` events). ckb_profile_end waits for the last one and returns, per launch in issue
+ * order, the kernel's name (32-byte slots) and its device time in ms. */
+int ckb_profile_begin(ckb_ctx *ctx, int capacity);
+int ckb_profile_end(ckb_ctx *ctx, int max_entries, char *names, float *ms, int *n_out);
+
 /* Number of kernels the library has launched on this context since creation (bench.py's gpu_launches). */
 uint64_t ckb_launch_count(const ckb_ctx *ctx);
 
