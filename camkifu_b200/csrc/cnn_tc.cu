@@ -20,8 +20,8 @@
 // input is exact in bf16, so conv1 needs two). Narrow layers (N = 32) put W_hi | W_lo side by side in the B operand so
 // that A_hi is read from shared memory once for both (the MMA is shared-memory bound at N = 32).
 //
-// Kernel structure (one persistent CTA per SM, 192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer (single thread), warps 2-5 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
+// Kernel structure (one persistent CTA per SM, 320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (single thread), warps 2-9 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
 // mbarrier pipelines: A tile full/empty (double buffered), weight/A stage ring full/empty, accumulator full/empty
 // (two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
 #include <cuda_bf16.h>
@@ -199,8 +199,10 @@ __device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &lo)
 }
 
 // -------------------------------------------------------------------------------------------------- the layer kernel
+#define TC_EPI_WARPS 8                        // two epilogue warps per TMEM lane quarter, each takes every other column chunk
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
 template <class L>
-__global__ void __launch_bounds__(192, 1) cnn_tc_layer(const __grid_constant__ LayerArgs args)
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_constant__ LayerArgs args)
 {
     using D = Derived<L>;
     extern __shared__ uint8_t smem_raw[];
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(192, 1) cnn_tc_layer(const __grid_constant__ L
             mbar_init(b_afull + 8 * i, 1);
             mbar_init(b_aempty + 8 * i, 1);
             mbar_init(b_tfull + 8 * i, 1);
-            mbar_init(b_tempty + 8 * i, 4);
+            mbar_init(b_tempty + 8 * i, TC_EPI_WARPS);
         }
         mbar_init(b_wfull, 1);
         for (int i = 0; i < 8; i++) {
@@ -356,21 +358,22 @@ __global__ void __launch_bounds__(192, 1) cnn_tc_layer(const __grid_constant__ L
     } else {
         // ================================================= epilogue: TMEM -> registers -> bias / ReLU / split -> HBM
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // which column chunks (j = half, half + 2, ...) it handles
         const int row = q * 32 + lane;
         for (int i = 0; i < n_my; i++) {
-            const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
             const int acc = i & 1;
-            const long long p = tile * 128 + row;
-            const long long patch = p / L::HW_IN;
-            const int rem = (int)(p - patch * L::HW_IN);
+            const int p = tile * 128 + row;              // flat pixel of the input grid (< 2^31 for 64 frames)
+            const int patch = p / L::HW_IN;
+            const int rem = p - patch * L::HW_IN;
             const int y = rem / L::GW, x = rem - y * L::GW;
             const bool valid = patch < args.n_patches && y < L::OH && x < L::OW;
-            const long long opix = patch * (L::OH * L::OW) + y * L::OW + x;
+            const long long opix = (long long)patch * (L::OH * L::OW) + y * L::OW + x;
             mbar_wait(b_tfull + 8 * acc, (i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
 #pragma unroll 2
-            for (int j = 0; j < L::N / 8; j++) {
+            for (int j = half; j < L::N / 8; j += TC_EPI_WARPS / 4) {
                 float v[8];
                 tc_ld8(taddr + 8 * j, v);
                 if (L::CONCAT) {
@@ -669,7 +672,7 @@ static int launch_layer(ckb_ctx *ctx, const char *name, const void *in, long lon
     a.n_tiles = (int)((n_pixels + 127) / 128);
     a.n_patches = n_patches;
     const int grid = a.n_tiles < ctx->num_sms ? a.n_tiles : ctx->num_sms;
-    cnn_tc_layer<L><<<grid, 192, Derived<L>::SMEM, st>>>(a);
+    cnn_tc_layer<L><<<grid, TC_THREADS, Derived<L>::SMEM, st>>>(a);
     CKB_LAUNCH_CHECK(ctx, name);
     return CKB_OK;
 }

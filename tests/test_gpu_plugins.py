@@ -1,0 +1,117 @@
+"""The drop-in plugins on the GPU, driven the way VidProcessor.execute drives a finder, against the reference's golden
+vectors (recorded by running the unmodified reference, oracle/gen_golden.py) and against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from camkifu_b200 import plugins, synth, weights
+from camkifu_b200.harness import HeadlessVManager, run_frames
+
+pytestmark = pytest.mark.gpu
+CODE = {'E': 0, 'B': 1, 'W': 2}
+
+
+def codes(arr):
+    return np.vectorize(CODE.get)(arr).astype(np.uint8)
+
+
+def test_sfclustering_stream_matches_reference(golden):
+    """7 frames through _doframe -> _find: canonical image, running average, the bulk moves the controller received and
+    the final board are those of the reference's SfClustering (clustering_stream.npz)."""
+    g = golden("clustering_stream.npz")
+    vm = HeadlessVManager(g["mtx"])
+    sf = plugins.SfClusteringB200(vm)
+    for i in range(7):
+        sf.set_rng_seed(int(g["seeds"][i]))          # the golden run did cv2.setRNGSeed(seed) before every frame
+        n0 = len(vm.controller.piped)
+        sf._doframe(g["frames"][i].copy())
+        sf.total_f_processed += 1
+        assert np.array_equal(sf.goban_img, g["goban"][i])
+        bulk = [a for ins, a in vm.controller.piped[n0:] if ins == "bulk"]
+        got = np.array([(CODE[m.color], m.y, m.x) for m in bulk[0][0]], np.int32) if bulk else np.zeros((0, 3), np.int32)
+        assert np.array_equal(got, g["moves_%d" % i]), "frame %d" % i
+        if i == 1:
+            assert np.array_equal(sf.accu, g["accu_1"])
+    assert np.array_equal(sf.accu, g["accu_last"])
+    assert np.array_equal(codes(vm.controller.stones), g["board"])
+
+
+def test_sfclustering_find_stones_delegate(golden):
+    """The SfMeta delegate contract: find_stones(img, rs, re, cs, ce, **kwargs) -> object array of E/B/W, or None."""
+    g = golden("clustering_full.npz")
+    sf = plugins.SfClusteringB200(None)              # SfMeta passes vmanager=None (sf_meta.py:52)
+    for k in range(3):
+        sf.set_rng_seed(int(g["seeds"][k]))
+        st = sf.find_stones(g["goban_%d" % k])
+        assert st.dtype == object and st.shape == (19, 19)
+        assert np.array_equal(codes(st), g["stones_%d" % k])
+        assert all(v is plugins.E or v is plugins.B or v is plugins.W for v in st.ravel())
+    sf.set_rng_seed(int(g["seeds"][3]))
+    assert sf.find_stones(g["goban_sparse"]) is None  # density check failed in the reference too
+    sf.set_rng_seed(int(g["seeds"][4]))
+    st = sf.find_stones(g["goban_0"], rs=6, re=13, cs=12, ce=19, canvas=None)
+    if g["stones_region"][0, 0] != 255:
+        assert np.array_equal(codes(st), g["stones_region"])
+    # float32 input (what SfMeta hands over after its own averaging) takes the same path
+    sf.set_rng_seed(int(g["seeds"][0]))
+    st = sf.find_stones(g["goban_0"].astype(np.float32))
+    assert np.array_equal(codes(st), g["stones_0"])
+
+
+def test_sfneural_predict_all_matches_oracle(oracle):
+    """Still image (bg_init_frames = 0): frame 0 loads the net, frame 1 runs predict_all -> one bulk update with every
+    non-empty intersection seen at confidence > 0.6 (sf_neural.py:57-70)."""
+    frames, mtx, truth, _ = synth.make_clip(8, 3, 240, 320, new_board_every=100)
+    params = weights.glorot_params(seed=0, bias_scale=0.5)
+    vm = HeadlessVManager(mtx, video="snapshot.png")
+    plugins.SfNeuralB200.cnn_params = params
+    try:
+        sf = plugins.SfNeuralB200(vm)
+        ctl = run_frames(sf, frames[:2])
+    finally:
+        plugins.SfNeuralB200.cnn_params = None
+    assert sf.has_sampled and len(ctl.bulk_moves()) == 1
+    y = oracle.c_cnn_forward(oracle.c_nn_gather(sf.goban_img), params)
+    stones, conf, keep = oracle.c_nn_decode(y)
+    sure = np.abs(conf - 0.6) > 1e-3                  # intersections whose keep flag is not within tolerance of the rule
+    got = {(r, c): col for col, r, c in ctl.bulk_moves()[0]}
+    for r in range(19):
+        for c in range(19):
+            if sure[r, c]:
+                assert ((r, c) in got) == bool(keep[r, c])
+                if keep[r, c]:
+                    assert CODE[got[(r, c)]] == stones[r, c]
+    # cache API of the reference's NNCache
+    sq, cf = sf.cache.predict_4_stones(3, 4)
+    assert np.array_equal(codes(sq), stones[6:8, 8:10]) and abs(cf - conf[6, 8]) < 1e-3
+    # steady state: a third frame showing the same position adds nothing contradictory
+    run_frames(sf, frames[2:3])
+    board = codes(ctl.stones)
+    assert np.array_equal(board[sure & keep], stones[sure & keep])
+
+
+def test_detect_pipeline_matches_engine(oracle):
+    from camkifu_b200.engine import StoneEngine, rng_seed, rng_advance
+    from camkifu_b200.pipeline import DetectPipeline, pinned_frames
+    H, W, n = 360, 480, 21
+    frames, mtx, truth, _ = synth.make_clip(3, n, H, W)
+    params = weights.glorot_params(seed=0)
+    pipe = DetectPipeline(H, W, mode="both", sub_batch=8, cnn_params=params)
+    host = pinned_frames(n, H, W)
+    host.copy_(torch.from_numpy(frames))
+    st0 = rng_seed(9)
+    res = {k: v.copy() for k, v in pipe.detect(host, mtx, rng_state=st0).items()}
+    assert pipe.h2d_bytes < n * H * W * 3            # only the board's bounding box travels
+    res_full = pipe.detect(frames, mtx, rng_state=st0, crop=False)   # pageable numpy input, whole frames
+    for k in res:
+        assert np.array_equal(res[k], res_full[k]), k
+    eng = pipe.eng
+    goban = eng.warp(torch.from_numpy(frames).cuda(), mtx)
+    ref = eng.cnn_forward(goban)
+    km = eng.find_stones(goban, [rng_advance(st0, i) for i in range(n)])
+    assert np.array_equal(res["stones"], ref["stones"].cpu().numpy())
+    assert np.array_equal(res["keep"], ref["keep"].cpu().numpy())
+    assert np.array_equal(res["km_stones"], km["stones"].cpu().numpy())
+    assert np.array_equal(res["km_stones"], truth)   # the k-means path reads these synthetic boards perfectly
+    g0 = goban[0].cpu().numpy()
+    assert np.array_equal(g0, oracle.c_warp(frames[0], mtx, 380))
