@@ -38,31 +38,31 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
 struct Conv1Cfg {   // input: 16-channel "row window" expansion of the patch (k = dx*3 + c), taps = dy
     static constexpr int NTAPS = 5, GW = 40, HW_IN = 1600, OH = 36, OW = 36, KC = 2, N = 32, A_PLANES = 1;
     static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
-    static constexpr int KCS = 2, NSTAGE = 1;
+    static constexpr int KCS = 2, NSTAGE = 1, NABUF = 6, NACC = 4;   // tiny tiles: latency bound without depth
     __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
 };
 struct Conv2Cfg {
     static constexpr int NTAPS = 25, GW = 36, HW_IN = 1296, OH = 32, OW = 32, KC = 4, N = 32, A_PLANES = 2;
     static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
-    static constexpr int KCS = 4, NSTAGE = 1;
+    static constexpr int KCS = 4, NSTAGE = 1, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 5) * 36 + t % 5; }
 };
 struct Conv3Cfg {
     static constexpr int NTAPS = 9, GW = 16, HW_IN = 256, OH = 14, OW = 14, KC = 4, N = 96, A_PLANES = 2;
     static constexpr bool CONCAT = false, A_RES = true, W_RES = true, OUT_F32 = false;
-    static constexpr int KCS = 4, NSTAGE = 1;
+    static constexpr int KCS = 4, NSTAGE = 1, NABUF = 3, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 16 + t % 3; }
 };
 struct Conv4Cfg {
     static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
     static constexpr bool CONCAT = false, A_RES = true, W_RES = false, OUT_F32 = false;
-    static constexpr int KCS = 6, NSTAGE = 4;
+    static constexpr int KCS = 6, NSTAGE = 4, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
 };
 struct Fc1Cfg {     // "pixels" are patches; tap q = pooled pixel, its A tile is streamed with its weights
     static constexpr int NTAPS = 36, GW = 1, HW_IN = 1, OH = 1, OW = 1, KC = 12, N = 160, A_PLANES = 2;
     static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true;
-    static constexpr int KCS = 4, NSTAGE = 5;
+    static constexpr int KCS = 4, NSTAGE = 5, NABUF = 0, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int) { return 0; }
 };
 
@@ -71,7 +71,8 @@ struct Derived {
     static constexpr int HALO = L::A_RES ? L::tapoff(L::NTAPS - 1) : 0;
     static constexpr int APLANE = ((128 + HALO) * 16 + 127) / 128 * 128;         // bytes of one A plane in smem
     static constexpr int A_TILE = L::A_RES ? L::A_PLANES * L::KC * APLANE : 0;   // one resident A tile
-    static constexpr int NABUF = L::A_RES ? 2 : 0;
+    static constexpr int NABUF = L::A_RES ? L::NABUF : 0;
+    static constexpr int NACC = L::NACC;
     static constexpr int NB = 2 * L::N;                                          // B rows: W_hi | W_lo
     static constexpr int W_TAP = L::KC * NB * 16;                                // bytes of one tap's weights
     static constexpr int W_ALL = L::W_RES ? L::NTAPS * W_TAP : 0;
@@ -81,11 +82,11 @@ struct Derived {
     static constexpr int STAGE = W_STAGE + A_STAGE;
     static constexpr int NSTAGE = (L::W_RES && L::A_RES) ? 0 : L::NSTAGE;
     static constexpr int ACC_COLS = L::CONCAT ? 2 * L::N : L::N;
-    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
-                                     : 2 * ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int SMEM = NABUF * A_TILE + W_ALL + NSTAGE * STAGE + 256 /*barriers*/ + 128 /*align*/;
+    static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
+                                     : NACC * ACC_COLS <= 256 ? 256 : 512;
+    static constexpr int SMEM = NABUF * A_TILE + W_ALL + NSTAGE * STAGE + 320 /*barriers*/ + 128 /*align*/;
     static_assert(L::KC % L::KCS == 0 && L::KCS % 2 == 0, "stages hold whole K=16 steps");
-    static_assert(2 * ACC_COLS <= 512, "two accumulators must fit in TMEM");
+    static_assert(NACC * ACC_COLS <= 512 && NACC <= 4 && NABUF <= 6, "accumulators must fit in TMEM; barrier map");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(L::N % 16 == 0 && NB <= 512, "UMMA N constraints (M = 128)");
 };
@@ -212,23 +213,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
     uint8_t *sS = sW + D::W_ALL;                         // NSTAGE x STAGE   (W part first, then A part)
     uint64_t *bars = (uint64_t *)(sS + D::NSTAGE * D::STAGE);
     // barrier map
-    const uint32_t b_afull = smem_u32(bars + 0);         // [2]
-    const uint32_t b_aempty = smem_u32(bars + 2);        // [2]
-    const uint32_t b_tfull = smem_u32(bars + 4);         // [2] accumulator ready
-    const uint32_t b_tempty = smem_u32(bars + 6);        // [2] accumulator drained
-    const uint32_t b_wfull = smem_u32(bars + 8);         // resident weights landed
-    const uint32_t b_sfull = smem_u32(bars + 9);         // [NSTAGE]
-    const uint32_t b_sempty = smem_u32(bars + 9 + 8);    // [NSTAGE]
-    uint32_t *tmem_slot = (uint32_t *)(bars + 26);
+    const uint32_t b_afull = smem_u32(bars + 0);         // [NABUF <= 6]
+    const uint32_t b_aempty = smem_u32(bars + 6);        // [NABUF]
+    const uint32_t b_tfull = smem_u32(bars + 12);        // [NACC <= 4] accumulator ready
+    const uint32_t b_tempty = smem_u32(bars + 16);       // [NACC] accumulator drained
+    const uint32_t b_wfull = smem_u32(bars + 20);        // resident weights landed
+    const uint32_t b_sfull = smem_u32(bars + 21);        // [NSTAGE <= 8]
+    const uint32_t b_sempty = smem_u32(bars + 29);       // [NSTAGE]
+    uint32_t *tmem_slot = (uint32_t *)(bars + 37);
     static_assert(D::NSTAGE <= 8, "barrier map");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = ((int)args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 6; i++) {
             mbar_init(b_afull + 8 * i, 1);
             mbar_init(b_aempty + 8 * i, 1);
+        }
+        for (int i = 0; i < 4; i++) {
             mbar_init(b_tfull + 8 * i, 1);
             mbar_init(b_tempty + 8 * i, TC_EPI_WARPS);
         }
@@ -263,9 +266,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
             uint32_t sit = 0;  // stage counter
             for (int i = 0; i < n_my; i++) {
                 const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
-                if (L::A_RES) {
-                    const int ab = i & 1;
-                    mbar_wait(b_aempty + 8 * ab, ((i >> 1) & 1) ^ 1);
+                if constexpr (L::A_RES) {
+                    const int ab = i % D::NABUF;
+                    mbar_wait(b_aempty + 8 * ab, ((i / D::NABUF) & 1) ^ 1);
                     mbar_expect_tx(b_afull + 8 * ab, (uint32_t)(L::A_PLANES * L::KC * (128 + D::HALO) * 16));
                     for (int pl = 0; pl < L::A_PLANES * L::KC; pl++)
                         bulk_g2s(smem_u32(sA + ab * D::A_TILE + pl * D::APLANE),
@@ -302,11 +305,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
             if (L::W_RES) mbar_wait(b_wfull, 0);
             uint32_t sit = 0;
             for (int i = 0; i < n_my; i++) {
-                const int acc = i & 1;
+                const int acc = i % D::NACC;
                 const uint32_t d_tmem = tmem_base + acc * D::ACC_COLS;
-                mbar_wait(b_tempty + 8 * acc, ((i >> 1) & 1) ^ 1);
-                const int ab = i & 1;
-                if (L::A_RES) mbar_wait(b_afull + 8 * ab, (i >> 1) & 1);
+                mbar_wait(b_tempty + 8 * acc, ((i / D::NACC) & 1) ^ 1);
+                const int ab = L::A_RES ? i % (L::A_RES ? D::NABUF : 1) : 0;
+                if (L::A_RES) mbar_wait(b_afull + 8 * ab, (i / (L::A_RES ? D::NABUF : 1)) & 1);
                 tc_fence_after();
                 uint32_t first = 1;
                 for (int t = 0; t < L::NTAPS; t++)
@@ -362,14 +365,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
         const int row = q * 32 + lane;
         for (int i = 0; i < n_my; i++) {
             const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int acc = i & 1;
+            const int acc = i % D::NACC;
             const int p = tile * 128 + row;              // flat pixel of the input grid (< 2^31 for 64 frames)
             const int patch = p / L::HW_IN;
             const int rem = p - patch * L::HW_IN;
             const int y = rem / L::GW, x = rem - y * L::GW;
             const bool valid = patch < args.n_patches && y < L::OH && x < L::OW;
             const long long opix = (long long)patch * (L::OH * L::OW) + y * L::OW + x;
-            mbar_wait(b_tfull + 8 * acc, (i >> 1) & 1);
+            mbar_wait(b_tfull + 8 * acc, (i / D::NACC) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
 #pragma unroll 2
