@@ -1,0 +1,65 @@
+"""N > 1 host logic on CPU: shard ranges, per-shard streaming state, and the final gather over gloo (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from camkifu_b200 import sharding
+
+
+def test_shard_ranges_cover_and_align():
+    for n in (0, 1, 2, 3, 10, 100, 1000, 100000):
+        for world in (1, 2, 4, 8):
+            got = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            for (a, b), (c, d) in zip(got, got[1:]):
+                assert b == c and a <= b
+            assert all(a % 3 == 0 for a, b in got if a < n)
+            sizes = [b - a for a, b in got]
+            assert max(sizes) - min(sizes) <= 3 or n < 3 * world
+    assert sharding.halo_start(0) == 0 and sharding.halo_start(300) == 219 and sharding.halo_start(300) % 3 == 0
+
+
+def test_rng_state_replay(oracle):
+    """The RNG state at frame f equals the state after the k-means calls of frames 0, 3, ..., < f (39 draws each)."""
+    px = np.random.default_rng(0).integers(0, 256, (400, 3)).astype(np.float32)
+    st = oracle.rng_seed_state(5)
+    states = {}
+    s = st
+    for f in range(0, 13, 3):
+        states[f] = s
+        s = oracle.c_kmeans(px, s)[3]
+    for f, want in states.items():
+        assert sharding.rng_state_at(st, f) == want
+    assert sharding.kmeans_calls_before(4) == 2 and sharding.kmeans_calls_before(6) == 2
+
+
+def _worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = sharding.shard_range(n, rank, world)
+        frames = torch.arange(a, b, dtype=torch.int64)
+        local = ((frames[:, None] * 7 + torch.arange(361)[None, :]) % 3).to(torch.uint8)   # fake board states
+        full = sharding.gather_board_states(local, n)
+        want = ((torch.arange(n)[:, None] * 7 + torch.arange(361)[None, :]) % 3).to(torch.uint8)
+        out[rank] = bool(torch.equal(full, want))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 64])
+def test_gather_board_states_gloo_world2(n):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
+    assert out[0] and out[1]
