@@ -259,14 +259,15 @@ def run_b200(args, rank, world, local_rank):
     kern = sorted(((n, v[0] / v[1], v[1]) for n, v in agg.items()), key=lambda x: -x[1] * x[2])
     ksum = sum(v[0] for v in agg.values())
     peaks = measured_peaks()
-    conv2_ms = agg["cnn_tc_conv2"][0] / agg["cnn_tc_conv2"][1]
+    c2name = "cnn_tc_conv2_pool" if "cnn_tc_conv2_pool" in agg else "cnn_tc_conv2"
+    conv2_ms = agg[c2name][0] / agg[c2name][1]
     conv2_flop = 2.0 * CNN_MAC_PER_PATCH["conv2"] * 100 * BATCH
     achieved = conv2_flop / (conv2_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "cnn_tc_layer<Conv2Cfg> (cnn_tc_conv2)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": c2name, "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": CONV2_DRAM_TRAFFIC_BYTES, "peak_source": peaks["source"],
                 "algorithmic_flop_per_launch": conv2_flop, "ms_per_launch": conv2_ms,
-                "share_of_step": agg["cnn_tc_conv2"][0] / ksum,
+                "share_of_step": agg[c2name][0] / ksum,
                 "note": "algorithmic FLOP = 2 x 26 214 400 MAC x 6400 patches; the kernel issues 3 bf16 products per MAC "
                         "(hi/lo operand split for the 1e-3 softmax bar), so 1/3 is its ceiling in these units"}
     cnn_flop = 2.0 * sum(CNN_MAC_PER_PATCH.values()) * 100 * BATCH

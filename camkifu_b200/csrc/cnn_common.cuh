@@ -36,6 +36,7 @@ struct ckb_cnn_weights {
     float *d_params;   // the flat fp32 blob (biases, fc2 and the SIMT verification path read it)
     void *d_tc;        // tensor-core operand planes (cnn_tc.cu)
     size_t tc_bytes;
+    int flat_conv2;    // debug: use the flattened-grid conv2 + separate pooling kernel
 };
 
 // patch origin of region (i, j): NNManager._get_rect_nn(*_subregion(i, j)) (nn_manager.py:92-126,256-275): 40 i, except

@@ -24,7 +24,10 @@
 // issuer (single thread), warps 2-9 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
 // mbarrier pipelines: A tile full/empty (double buffered), weight/A stage ring full/empty, accumulator full/empty
 // (two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include <new>
 
@@ -49,13 +52,13 @@ struct Conv2Cfg {
 };
 struct Conv3Cfg {
     static constexpr int NTAPS = 9, GW = 16, HW_IN = 256, OH = 14, OW = 14, KC = 4, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = false, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 3, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 16 + t % 3; }
 };
 struct Conv4Cfg {
     static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = false, A_RES = true, W_RES = false, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false;
     static constexpr int KCS = 6, NSTAGE = 4, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
 };
@@ -169,10 +172,18 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 
 // un-swizzled K-major shared memory matrix descriptor: 8-row x 16-byte core matrices, rows 16 B apart,
 // SBO (next 8 rows) = 128 B, LBO (next 8 K elements) = lbo_bytes; descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 128u)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// 4-D tiled tensor-map load (TMA): box -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
 }
 // instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc(int n)
@@ -419,6 +430,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
     }
 }
 
+
+// ------------------------------------------------------------------------------- conv2 + 2x2 max-pool on 2-D tiles
+// conv2 is half of the network's MACs. Instead of 128 consecutive pixels of the flattened 36-wide grid (21 % of which
+// are not outputs), a tile here is an 8 x 16 block of OUTPUT pixels: the tensor-map TMA load brings the 12 x 20 input
+// window of all 8 planes in one instruction, laid out [plane][row][12 px][16 B]; the A descriptor's 8-row core matrices
+// are the 8 pixels of one tile row and its stride between row groups (SBO) is the window's row pitch (192 B), so MMA row
+// m = 8 * (tile row) + (tile column). Every row is a valid output, and the four pixels of a pooling window sit in lanes
+// l, l+1, l+8, l+9 of one warp: the 2x2 max is two shuffles in the epilogue and only the pooled 16 x 16 x 32 map is
+// written (no conv2 output round trip through HBM, no pooling kernel).
+struct Conv2PArgs {
+    const uint4 *w;      // Conv2Cfg packing: [tap 25][chunk 4][row 64 = W_hi | W_lo][8]
+    const float *bias;
+    uint4 *out;          // pooled planes [2][4][out_plane], pixel = patch*256 + y*16 + x
+    long long out_plane;
+    int n_tiles;         // patches * 8
+};
+
+#define C2P_ROWPITCH 192                     // 12 pixels x 16 B
+#define C2P_PLANE (20 * C2P_ROWPITCH)        // 3840 B
+#define C2P_TILE (8 * C2P_PLANE)             // 30720 B: 4 chunks x (hi, lo)
+#define C2P_NABUF 3
+#define C2P_W (25 * 4 * 64 * 16)             // 102400 B
+#define C2P_SMEM (C2P_NABUF * C2P_TILE + C2P_W + 320 + 128)
+
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_constant__ CUtensorMap tmap,
+                                                                   const __grid_constant__ Conv2PArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *sA = smem;
+    uint8_t *sW = sA + C2P_NABUF * C2P_TILE;
+    uint64_t *bars = (uint64_t *)(sW + C2P_W);
+    const uint32_t b_afull = smem_u32(bars + 0), b_aempty = smem_u32(bars + 4), b_tfull = smem_u32(bars + 8),
+                   b_tempty = smem_u32(bars + 10), b_wfull = smem_u32(bars + 12);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 13);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C2P_NABUF; i++) { mbar_init(b_afull + 8 * i, 1); mbar_init(b_aempty + 8 * i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(b_tfull + 8 * i, 1); mbar_init(b_tempty + 8 * i, TC_EPI_WARPS); }
+        mbar_init(b_wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            mbar_expect_tx(b_wfull, C2P_W);
+            for (int off = 0; off < C2P_W; off += 25600) bulk_g2s(smem_u32(sW + off), (const uint8_t *)args.w + off, 25600, b_wfull);
+            for (int i = 0; i < n_my; i++) {
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+                const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
+                const int ab = i % C2P_NABUF;
+                mbar_wait(b_aempty + 8 * ab, ((i / C2P_NABUF) & 1) ^ 1);
+                mbar_expect_tx(b_afull + 8 * ab, C2P_TILE);
+                tma_load_4d(smem_u32(sA + ab * C2P_TILE), &tmap, 0, 8 * st, patch * 36 + 16 * rb, 0, b_afull + 8 * ab);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC64 = umma_idesc(64), IDESC32 = umma_idesc(32);
+            mbar_wait(b_wfull, 0);
+            for (int i = 0; i < n_my; i++) {
+                const int acc = i & 1, ab = i % C2P_NABUF;
+                const uint32_t d_tmem = tmem_base + acc * 64;
+                mbar_wait(b_tempty + 8 * acc, ((i >> 1) & 1) ^ 1);
+                mbar_wait(b_afull + 8 * ab, (i / C2P_NABUF) & 1);
+                tc_fence_after();
+                const uint32_t a_tile = smem_u32(sA + ab * C2P_TILE);
+                uint32_t first = 1;
+#pragma unroll 1
+                for (int t = 0; t < 25; t++) {
+                    const uint32_t a_hi = a_tile + ((t / 5) * 12 + (t % 5)) * 16;
+                    const uint32_t wb = smem_u32(sW) + t * (4 * 64 * 16);
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; k2++) {
+                        const uint64_t db = umma_desc(wb + 2 * k2 * 64 * 16, 64 * 16);
+                        tc_mma_bf16(d_tmem, umma_desc(a_hi + 2 * k2 * C2P_PLANE, C2P_PLANE, C2P_ROWPITCH), db, IDESC64, first ^ 1);
+                        tc_mma_bf16(d_tmem, umma_desc(a_hi + (4 + 2 * k2) * C2P_PLANE, C2P_PLANE, C2P_ROWPITCH), db, IDESC32, 1);
+                        first = 0;
+                    }
+                }
+                tc_commit(b_aempty + 8 * ab);
+                tc_commit(b_tfull + 8 * acc);
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int trow = q * 4 + (lane >> 3), tcol = lane & 7;        // position inside the 16 x 8 output tile
+        const bool writer = (lane & 9) == 0;                          // even row, even column: owns the pooled pixel
+        for (int i = 0; i < n_my; i++) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
+            const int acc = i & 1;
+            const long long opix = (long long)patch * 256 + (8 * rb + (trow >> 1)) * 16 + 4 * st + (tcol >> 1);
+            mbar_wait(b_tfull + 8 * acc, (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
+#pragma unroll
+            for (int j = half; j < 4; j += 2) {
+                float v[8], u[8];
+                tc_ld8(taddr + 8 * j, v);
+                tc_ld8(taddr + 32 + 8 * j, u);
+                tc_ld_wait();
+                const float4 b0 = __ldg((const float4 *)args.bias + 2 * j), b1 = __ldg((const float4 *)args.bias + 2 * j + 1);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float x = fmaxf(v[k] + u[k] + bb[k], 0.f);
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                    v[k] = x;
+                }
+                if (writer) {
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    args.out[(long long)j * args.out_plane + opix] = hi;
+                    args.out[(long long)(4 + j) * args.out_plane + opix] = lo;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------- elementwise companions
 // conv1 input: per patch pixel the 16-channel row window k = dx*3 + c (dx < 5, c < 3; k = 15 and windows that leave the
 // patch are zero), uint8 -> bf16 (exact). Output planes [chunk 0|1][P*1600 (+pad)][8]. Reads the canonical image in
@@ -609,6 +760,9 @@ int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv3Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv3Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Fc1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Fc1Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_conv2_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, C2P_SMEM));
+    const char *flat = getenv("CKB_CNN_FLAT_CONV2");
+    ctx->cnn->flat_conv2 = flat && flat[0] == '1';
     return CKB_OK;
 }
 
@@ -680,6 +834,50 @@ static int launch_layer(ckb_ctx *ctx, const char *name, const void *in, long lon
     return CKB_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// conv2 on 2-D tiles + fused pooling: a1 planes [8][a1_plane] viewed as (8 ch, 36 x, 36*P y, 8 planes)
+static int launch_conv2_pool(ckb_ctx *ctx, const void *a1, long long a1_plane, size_t off_w, size_t off_b, void *p2,
+                             long long p2_plane, int n_patches, cudaStream_t st)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) CKB_FAIL(ctx, CKB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {8, 36, (cuuint64_t)36 * n_patches, 8};
+    const cuuint64_t gstr[3] = {16, 36 * 16, (cuuint64_t)a1_plane * 16};
+    const cuuint32_t box[4] = {8, 12, 20, 8};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a1), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CKB_FAIL(ctx, CKB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    Conv2PArgs a;
+    a.w = (const uint4 *)((const uint8_t *)ctx->cnn->d_tc + off_w);
+    a.bias = (const float *)((const uint8_t *)ctx->cnn->d_tc + off_b);
+    a.out = (uint4 *)p2;
+    a.out_plane = p2_plane;
+    a.n_tiles = n_patches * 8;
+    const int grid = a.n_tiles < ctx->num_sms ? a.n_tiles : ctx->num_sms;
+    cnn_tc_conv2_pool<<<grid, TC_THREADS, C2P_SMEM, st>>>(tmap, a);
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_conv2_pool");
+    return CKB_OK;
+}
+
 #define TC_TRY(call)                 \
     do {                             \
         const int rc__ = (call);     \
@@ -700,10 +898,14 @@ static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t
     CKB_LAUNCH_CHECK(ctx, "cnn_tc_expand_input");
     TC_TRY(launch_layer<Conv1Cfg>(ctx, "cnn_tc_conv1", x0, W.x0_plane, B.off_w[0], B.off_b[0], a1, W.a1_plane, nullptr,
                                   (long long)P * 1600, P, st));
-    TC_TRY(launch_layer<Conv2Cfg>(ctx, "cnn_tc_conv2", a1, W.a1_plane, B.off_w[1], B.off_b[1], a2, W.a2_plane, nullptr,
-                                  (long long)P * 1296, P, st));
-    cnn_tc_pool<32, 4, false><<<(unsigned)(((long long)P * 256 * 4 + 255) / 256), 256, 0, st>>>(a2, W.a2_plane, P, p2, W.p2_plane);
-    CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool2");
+    if (ctx->cnn->flat_conv2) {   // round-1 baseline formulation, kept for A/B measurements (CKB_CNN_FLAT_CONV2=1)
+        TC_TRY(launch_layer<Conv2Cfg>(ctx, "cnn_tc_conv2", a1, W.a1_plane, B.off_w[1], B.off_b[1], a2, W.a2_plane, nullptr,
+                                      (long long)P * 1296, P, st));
+        cnn_tc_pool<32, 4, false><<<(unsigned)(((long long)P * 256 * 4 + 255) / 256), 256, 0, st>>>(a2, W.a2_plane, P, p2, W.p2_plane);
+        CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool2");
+    } else {
+        TC_TRY(launch_conv2_pool(ctx, a1, W.a1_plane, B.off_w[1], B.off_b[1], p2, W.p2_plane, P, st));
+    }
     TC_TRY(launch_layer<Conv3Cfg>(ctx, "cnn_tc_conv3", p2, W.p2_plane, B.off_w[2], B.off_b[2], a3, W.a3_plane, nullptr,
                                   (long long)P * 256, P, st));
     TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
