@@ -177,6 +177,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// Descriptors in the issue loops are assembled from a precomputed low word (start address | LBO) plus compile-time
+// offsets and a constant high word (SBO | version), so that one MMA costs ~3 issue slots (see tools/mma_probe.cu: the
+// tensor core retires an M = 128, K = 16 MMA every max(53, N/2) cycles; the issuing thread must stay below that).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// one elected lane of a converged warp (the warp index must be warp-uniform for the compiler: see warp_index())
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 // 4-D tiled tensor-map load (TMA): box -> shared memory, completion on an mbarrier
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c0, int c1, int c2, int c3, uint32_t bar)
 {
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
     uint32_t *tmem_slot = (uint32_t *)(bars + 37);
     static_assert(D::NSTAGE <= 8, "barrier map");
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index(), lane = threadIdx.x & 31;
     const int n_my = ((int)args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
 
     if (warp == 0) {
         // ============================================================ producer: TMA bulk copies, one elected thread
-        if (lane == 0) {
+        if (elect_one()) {
             if (L::W_RES) {
                 mbar_expect_tx(b_wfull, (uint32_t)D::W_ALL);
                 constexpr int PIECE = 32768;
@@ -310,9 +324,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
         }
     } else if (warp == 1) {
         // =============================================================== MMA issuer: one thread drives the tensor core
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t IDESC_WIDE = umma_idesc(L::CONCAT ? 2 * L::N : L::N);
             constexpr uint32_t IDESC_N = umma_idesc(L::N);
+            constexpr uint32_t HI = desc_hi(128);
+            constexpr uint32_t A_LBO = L::A_RES ? D::APLANE : 2048;
+            constexpr uint32_t A_LO_OFF = (L::A_RES ? L::KC * D::APLANE : L::KCS * 2048) >> 4;   // hi plane -> lo plane
+            constexpr uint32_t A_STEP = (2 * A_LBO) >> 4, W_STEP = (2 * D::NB * 16) >> 4;       // one K = 16 step
             if (L::W_RES) mbar_wait(b_wfull, 0);
             uint32_t sit = 0;
             for (int i = 0; i < n_my; i++) {
@@ -322,41 +340,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
                 const int ab = L::A_RES ? i % (L::A_RES ? D::NABUF : 1) : 0;
                 if (L::A_RES) mbar_wait(b_afull + 8 * ab, (i / (L::A_RES ? D::NABUF : 1)) & 1);
                 tc_fence_after();
+                const uint32_t a_tile_lo = desc_lo(smem_u32(sA + ab * D::A_TILE), A_LBO);
+                const uint32_t w_res_lo = desc_lo(smem_u32(sW), D::NB * 16);
                 uint32_t first = 1;
+#pragma unroll(L::A_RES ? L::NTAPS : 1)
                 for (int t = 0; t < L::NTAPS; t++)
+#pragma unroll
                     for (int g = 0; g < D::SPT; g++) {
-                        uint32_t a_hi, a_lbo, a_lo_off, w_base;
+                        uint32_t a_lo, w_lo;
                         if constexpr (D::NSTAGE > 0) {
                             const int s = sit % D::NSTAGE;
                             mbar_wait(b_sfull + 8 * s, (sit / D::NSTAGE) & 1);
                             tc_fence_after();
-                            w_base = smem_u32(sS + s * D::STAGE);
+                            const uint32_t stage = smem_u32(sS + s * D::STAGE);
+                            w_lo = desc_lo(stage, D::NB * 16);
+                            a_lo = L::A_RES ? 0u : desc_lo(stage + D::W_STAGE, A_LBO);
                         } else {
-                            w_base = smem_u32(sW + t * D::W_TAP + g * L::KCS * D::NB * 16);
+                            w_lo = w_res_lo + (uint32_t)((t * D::W_TAP + g * L::KCS * D::NB * 16) >> 4);
                         }
-                        if (L::A_RES) {
-                            a_hi = smem_u32(sA + ab * D::A_TILE + g * L::KCS * D::APLANE) + L::tapoff(t) * 16;
-                            a_lbo = D::APLANE;
-                            a_lo_off = L::KC * D::APLANE;
-                        } else {
-                            a_hi = w_base + D::W_STAGE;
-                            a_lbo = 2048;
-                            a_lo_off = L::KCS * 2048;
-                        }
+                        if (L::A_RES) a_lo = a_tile_lo + (uint32_t)((g * L::KCS * D::APLANE + L::tapoff(t) * 16) >> 4);
 #pragma unroll
                         for (int k2 = 0; k2 < L::KCS / 2; k2++) {
-                            const uint64_t da = umma_desc(a_hi + 2 * k2 * a_lbo, a_lbo);
-                            const uint64_t db = umma_desc(w_base + 2 * k2 * D::NB * 16, D::NB * 16);
+                            const uint64_t da = desc64(a_lo + k2 * A_STEP, HI);
+                            const uint64_t db = desc64(w_lo + k2 * W_STEP, HI);
                             if (L::CONCAT) {
                                 tc_mma_bf16(d_tmem, da, db, IDESC_WIDE, first ^ 1);           // A_hi [W_hi | W_lo]
                                 if (L::A_PLANES == 2)
-                                    tc_mma_bf16(d_tmem, umma_desc(a_hi + a_lo_off + 2 * k2 * a_lbo, a_lbo), db, IDESC_N, 1);
+                                    tc_mma_bf16(d_tmem, desc64(a_lo + A_LO_OFF + k2 * A_STEP, HI), db, IDESC_N, 1);
                             } else {
                                 tc_mma_bf16(d_tmem, da, db, IDESC_N, first ^ 1);              // A_hi W_hi
-                                tc_mma_bf16(d_tmem, da, umma_desc(w_base + 2 * k2 * D::NB * 16 + L::N * 16, D::NB * 16),
-                                            IDESC_N, 1);                                       // A_hi W_lo
+                                tc_mma_bf16(d_tmem, da, desc64(w_lo + k2 * W_STEP + ((L::N * 16) >> 4), HI), IDESC_N, 1);   // A_hi W_lo
                                 if (L::A_PLANES == 2)
-                                    tc_mma_bf16(d_tmem, umma_desc(a_hi + a_lo_off + 2 * k2 * a_lbo, a_lbo), db, IDESC_N, 1);
+                                    tc_mma_bf16(d_tmem, desc64(a_lo + A_LO_OFF + k2 * A_STEP, HI), db, IDESC_N, 1);
                             }
                             first = 0;
                         }
@@ -465,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_
     const uint32_t b_afull = smem_u32(bars + 0), b_aempty = smem_u32(bars + 4), b_tfull = smem_u32(bars + 8),
                    b_tempty = smem_u32(bars + 10), b_wfull = smem_u32(bars + 12);
     uint32_t *tmem_slot = (uint32_t *)(bars + 13);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index(), lane = threadIdx.x & 31;
     const int n_my = (args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             mbar_expect_tx(b_wfull, C2P_W);
             for (int off = 0; off < C2P_W; off += 25600) bulk_g2s(smem_u32(sW + off), (const uint8_t *)args.w + off, 25600, b_wfull);
@@ -498,8 +513,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t IDESC64 = umma_idesc(64), IDESC32 = umma_idesc(32);
+            constexpr uint32_t A_HI = desc_hi(C2P_ROWPITCH), W_HI = desc_hi(128);
+            const uint32_t w_lo = desc_lo(smem_u32(sW), 64 * 16);
             mbar_wait(b_wfull, 0);
             for (int i = 0; i < n_my; i++) {
                 const int acc = i & 1, ab = i % C2P_NABUF;
@@ -507,18 +524,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_
                 mbar_wait(b_tempty + 8 * acc, ((i >> 1) & 1) ^ 1);
                 mbar_wait(b_afull + 8 * ab, (i / C2P_NABUF) & 1);
                 tc_fence_after();
-                const uint32_t a_tile = smem_u32(sA + ab * C2P_TILE);
-                uint32_t first = 1;
-#pragma unroll 1
+                const uint32_t a_lo = desc_lo(smem_u32(sA + ab * C2P_TILE), C2P_PLANE);
+#pragma unroll
                 for (int t = 0; t < 25; t++) {
-                    const uint32_t a_hi = a_tile + ((t / 5) * 12 + (t % 5)) * 16;
-                    const uint32_t wb = smem_u32(sW) + t * (4 * 64 * 16);
 #pragma unroll
                     for (int k2 = 0; k2 < 2; k2++) {
-                        const uint64_t db = umma_desc(wb + 2 * k2 * 64 * 16, 64 * 16);
-                        tc_mma_bf16(d_tmem, umma_desc(a_hi + 2 * k2 * C2P_PLANE, C2P_PLANE, C2P_ROWPITCH), db, IDESC64, first ^ 1);
-                        tc_mma_bf16(d_tmem, umma_desc(a_hi + (4 + 2 * k2) * C2P_PLANE, C2P_PLANE, C2P_ROWPITCH), db, IDESC32, 1);
-                        first = 0;
+                        const uint32_t ao = (uint32_t)((((t / 5) * 12 + (t % 5)) * 16 + 2 * k2 * C2P_PLANE) >> 4);
+                        const uint64_t db = desc64(w_lo + (uint32_t)((t * (4 * 64 * 16) + 2 * k2 * 64 * 16) >> 4), W_HI);
+                        tc_mma_bf16(d_tmem, desc64(a_lo + ao, A_HI), db, IDESC64, (t | k2) != 0);
+                        tc_mma_bf16(d_tmem, desc64(a_lo + ao + (uint32_t)((4 * C2P_PLANE) >> 4), A_HI), db, IDESC32, 1);
                     }
                 }
                 tc_commit(b_aempty + 8 * ab);
