@@ -12,7 +12,7 @@ of the reference architecture: the trained weights do not ship with the referenc
 `value`   frames/s with the frames resident in HBM, CUDA events on the launching stream, max over ranks.
 `e2e`     the same metric through camkifu_b200.pipeline.DetectPipeline.detect() with HOST (pinned) frames: H2D of the
           frames and D2H of the board states inside the timed region.
-`roofline` dominant kernel = the conv2 tensor-core layer; achieved = algorithmic FLOP / mean launch time measured with
+`roofline` dominant kernel = cnn_tc_front (patch gather + conv1 + conv2 + pool on tcgen05); achieved = algorithmic FLOP / mean launch time measured with
           CUDA events in the timed region (ckb_profile_begin/end); peak from MEASURED_PEAKS.json.
 `cpu_baseline` the reference's CPU path (cv2 warp + fp32 CNN, oracle/) on a bounded sample, timed on this host.
 `--impl reference` times that CPU path alone with all host threads and prints the same line with "impl": "reference".
@@ -38,9 +38,9 @@ WORKLOAD = "SfNeural CNN stone classification, synthetic 1080p 19x19 frames, 64 
 CNN_MAC_PER_PATCH = {"conv1": 36 * 36 * 75 * 32, "conv2": 32 * 32 * 800 * 32, "conv3": 14 * 14 * 288 * 90,
                      "conv4": 12 * 12 * 810 * 90, "fc1": 3240 * 160, "fc2": 160 * 81}
 assert sum(CNN_MAC_PER_PATCH.values()) == 45434080
-# dram__bytes_read.sum + dram__bytes_write.sum of one cnn_tc_conv2 launch (64 frames), from the ncu --set full capture
+# dram__bytes_read.sum + dram__bytes_write.sum of one cnn_tc_front launch (64 frames), from the ncu --set full capture
 # committed under profiles/ (None until a capture exists for the current kernel)
-CONV2_DRAM_TRAFFIC_BYTES = None
+FRONT_DRAM_TRAFFIC_BYTES = None
 
 
 def measured_peaks():
@@ -259,17 +259,18 @@ def run_b200(args, rank, world, local_rank):
     kern = sorted(((n, v[0] / v[1], v[1]) for n, v in agg.items()), key=lambda x: -x[1] * x[2])
     ksum = sum(v[0] for v in agg.values())
     peaks = measured_peaks()
-    c2name = "cnn_tc_conv2_pool" if "cnn_tc_conv2_pool" in agg else "cnn_tc_conv2"
-    conv2_ms = agg[c2name][0] / agg[c2name][1]
-    conv2_flop = 2.0 * CNN_MAC_PER_PATCH["conv2"] * 100 * BATCH
-    achieved = conv2_flop / (conv2_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": c2name, "achieved": achieved,
+    front = "cnn_tc_front"          # gather + conv1 + conv2 + pool: the dominant kernel
+    front_ms = agg[front][0] / agg[front][1]
+    front_flop = 2.0 * (CNN_MAC_PER_PATCH["conv1"] + CNN_MAC_PER_PATCH["conv2"]) * 100 * BATCH
+    achieved = front_flop / (front_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": front, "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": CONV2_DRAM_TRAFFIC_BYTES, "peak_source": peaks["source"],
-                "algorithmic_flop_per_launch": conv2_flop, "ms_per_launch": conv2_ms,
-                "share_of_step": agg[c2name][0] / ksum,
-                "note": "algorithmic FLOP = 2 x 26 214 400 MAC x 6400 patches; the kernel issues 3 bf16 products per MAC "
-                        "(hi/lo operand split for the 1e-3 softmax bar), so 1/3 is its ceiling in these units"}
+                "traffic": FRONT_DRAM_TRAFFIC_BYTES, "peak_source": peaks["source"],
+                "algorithmic_flop_per_launch": front_flop, "ms_per_launch": front_ms,
+                "share_of_step": agg[front][0] / ksum,
+                "note": "algorithmic FLOP = 2 x (3 110 400 conv1 + 26 214 400 conv2) MAC x 6400 patches; the kernel issues 3 "
+                        "bf16 products per conv2 MAC and 2 per conv1 MAC (hi/lo operand split for the 1e-3 softmax bar), "
+                        "so ~1/3 is its ceiling in these units"}
     cnn_flop = 2.0 * sum(CNN_MAC_PER_PATCH.values()) * 100 * BATCH
     cnn_ms = sum(v[0] for n, v in agg.items() if n.startswith("cnn_")) / args.steps
 

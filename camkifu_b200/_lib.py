@@ -36,6 +36,7 @@ SIGNATURES = {
     "ckb_cnn_forward_simt": (C.c_int, [C.c_void_p, _u8p, C.c_int, _vp, C.c_size_t, _f32p, _u8p, _f32p, _u8p,
                                        C.c_void_p]),
     "ckb_cnn_workspace_simt": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "ckb_cnn_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "ckb_cnn_debug_activation": (C.c_int, [C.c_void_p, _vp, C.c_int, C.c_int, _f32p, C.c_void_p]),
     "ckb_frame_roi": (C.c_int, [_f64p, C.c_int, C.c_int, C.c_int, _i32p]),
     "ckb_upload_frames": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _i32p, _u8p,

@@ -36,7 +36,7 @@ struct ckb_cnn_weights {
     float *d_params;   // the flat fp32 blob (biases, fc2 and the SIMT verification path read it)
     void *d_tc;        // tensor-core operand planes (cnn_tc.cu)
     size_t tc_bytes;
-    int flat_conv2;    // debug: use the flattened-grid conv2 + separate pooling kernel
+    int dump_a1;       // test aid: the front kernel also writes conv1 activations to the workspace
 };
 
 // patch origin of region (i, j): NNManager._get_rect_nn(*_subregion(i, j)) (nn_manager.py:92-126,256-275): 40 i, except
@@ -45,5 +45,8 @@ __host__ __device__ __forceinline__ int cnn_patch_origin(int i) { return i < 9 ?
 
 int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *h_params);   // cnn_tc.cu
 void ckb_cnn_tc_free(ckb_ctx *ctx);
+int ckb_cnn_front_init(ckb_ctx *ctx);                       // cnn_tc_front.cu
+int ckb_launch_cnn_front(ckb_ctx *ctx, const uint8_t *d_goban, int n_patches, const void *w1, const float *b1, const void *w2,
+                         const float *b2, void *p2, long long p2_plane, void *dbg_a1, long long a1_plane, cudaStream_t st);
 int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softmax_or_null, float *d_softmax_tmp,
                       uint8_t *d_stones, float *d_conf, uint8_t *d_keep, cudaStream_t st);

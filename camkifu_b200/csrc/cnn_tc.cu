@@ -24,14 +24,12 @@
 // issuer (single thread), warps 2-9 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
 // mbarrier pipelines: A tile full/empty (double buffered), weight/A stage ring full/empty, accumulator full/empty
 // (two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1).
-#include <cuda.h>
 #include <cuda_bf16.h>
-
-#include <stdlib.h>
 
 #include <new>
 
 #include "cnn_common.cuh"
+#include "tc_ptx.cuh"
 
 size_t ckb_cnn_simt_workspace(int n);
 int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, float *d_softmax, uint8_t *d_stones,
@@ -105,124 +103,6 @@ struct LayerArgs {
     int n_tiles;            // 128-pixel tiles of the input grid
     int n_patches;
 };
-
-// ------------------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float *v)
-{
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// un-swizzled K-major shared memory matrix descriptor: 8-row x 16-byte core matrices, rows 16 B apart,
-// SBO (next 8 rows) = 128 B, LBO (next 8 K elements) = lbo_bytes; descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 128u)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// Descriptors in the issue loops are assembled from a precomputed low word (start address | LBO) plus compile-time
-// offsets and a constant high word (SBO | version), so that one MMA costs ~3 issue slots (see tools/mma_probe.cu: the
-// tensor core retires an M = 128, K = 16 MMA every max(53, N/2) cycles; the issuing thread must stay below that).
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
-__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
-// one elected lane of a converged warp (the warp index must be warp-uniform for the compiler: see warp_index())
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
-// 4-D tiled tensor-map load (TMA): box -> shared memory, completion on an mbarrier
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c0, int c1, int c2, int c3, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc(int n)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
-{
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *(const uint32_t *)&v;
-}
-// x = hi + lo (+ O(2^-17 x)): hi = bf16(x), lo = bf16(x - hi)
-__device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &lo)
-{
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 // -------------------------------------------------------------------------------------------------- the layer kernel
 #define TC_EPI_WARPS 8                        // two epilogue warps per TMEM lane quarter, each takes every other column chunk
@@ -446,168 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
 }
 
 
-// ------------------------------------------------------------------------------- conv2 + 2x2 max-pool on 2-D tiles
-// conv2 is half of the network's MACs. Instead of 128 consecutive pixels of the flattened 36-wide grid (21 % of which
-// are not outputs), a tile here is an 8 x 16 block of OUTPUT pixels: the tensor-map TMA load brings the 12 x 20 input
-// window of all 8 planes in one instruction, laid out [plane][row][12 px][16 B]; the A descriptor's 8-row core matrices
-// are the 8 pixels of one tile row and its stride between row groups (SBO) is the window's row pitch (192 B), so MMA row
-// m = 8 * (tile row) + (tile column). Every row is a valid output, and the four pixels of a pooling window sit in lanes
-// l, l+1, l+8, l+9 of one warp: the 2x2 max is two shuffles in the epilogue and only the pooled 16 x 16 x 32 map is
-// written (no conv2 output round trip through HBM, no pooling kernel).
-struct Conv2PArgs {
-    const uint4 *w;      // Conv2Cfg packing: [tap 25][chunk 4][row 64 = W_hi | W_lo][8]
-    const float *bias;
-    uint4 *out;          // pooled planes [2][4][out_plane], pixel = patch*256 + y*16 + x
-    long long out_plane;
-    int n_tiles;         // patches * 8
-};
-
-#define C2P_ROWPITCH 192                     // 12 pixels x 16 B
-#define C2P_PLANE (20 * C2P_ROWPITCH)        // 3840 B
-#define C2P_TILE (8 * C2P_PLANE)             // 30720 B: 4 chunks x (hi, lo)
-#define C2P_NABUF 3
-#define C2P_W (25 * 4 * 64 * 16)             // 102400 B
-#define C2P_SMEM (C2P_NABUF * C2P_TILE + C2P_W + 320 + 128)
-
-__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_conv2_pool(const __grid_constant__ CUtensorMap tmap,
-                                                                   const __grid_constant__ Conv2PArgs args)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint8_t *sA = smem;
-    uint8_t *sW = sA + C2P_NABUF * C2P_TILE;
-    uint64_t *bars = (uint64_t *)(sW + C2P_W);
-    const uint32_t b_afull = smem_u32(bars + 0), b_aempty = smem_u32(bars + 4), b_tfull = smem_u32(bars + 8),
-                   b_tempty = smem_u32(bars + 10), b_wfull = smem_u32(bars + 12);
-    uint32_t *tmem_slot = (uint32_t *)(bars + 13);
-    const int warp = warp_index(), lane = threadIdx.x & 31;
-    const int n_my = (args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < C2P_NABUF; i++) { mbar_init(b_afull + 8 * i, 1); mbar_init(b_aempty + 8 * i, 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(b_tfull + 8 * i, 1); mbar_init(b_tempty + 8 * i, TC_EPI_WARPS); }
-        mbar_init(b_wfull, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            mbar_expect_tx(b_wfull, C2P_W);
-            for (int off = 0; off < C2P_W; off += 25600) bulk_g2s(smem_u32(sW + off), (const uint8_t *)args.w + off, 25600, b_wfull);
-            for (int i = 0; i < n_my; i++) {
-                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-                const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
-                const int ab = i % C2P_NABUF;
-                mbar_wait(b_aempty + 8 * ab, ((i / C2P_NABUF) & 1) ^ 1);
-                mbar_expect_tx(b_afull + 8 * ab, C2P_TILE);
-                tma_load_4d(smem_u32(sA + ab * C2P_TILE), &tmap, 0, 8 * st, patch * 36 + 16 * rb, 0, b_afull + 8 * ab);
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t IDESC64 = umma_idesc(64), IDESC32 = umma_idesc(32);
-            constexpr uint32_t A_HI = desc_hi(C2P_ROWPITCH), W_HI = desc_hi(128);
-            const uint32_t w_lo = desc_lo(smem_u32(sW), 64 * 16);
-            mbar_wait(b_wfull, 0);
-            for (int i = 0; i < n_my; i++) {
-                const int acc = i & 1, ab = i % C2P_NABUF;
-                const uint32_t d_tmem = tmem_base + acc * 64;
-                mbar_wait(b_tempty + 8 * acc, ((i >> 1) & 1) ^ 1);
-                mbar_wait(b_afull + 8 * ab, (i / C2P_NABUF) & 1);
-                tc_fence_after();
-                const uint32_t a_lo = desc_lo(smem_u32(sA + ab * C2P_TILE), C2P_PLANE);
-#pragma unroll
-                for (int t = 0; t < 25; t++) {
-#pragma unroll
-                    for (int k2 = 0; k2 < 2; k2++) {
-                        const uint32_t ao = (uint32_t)((((t / 5) * 12 + (t % 5)) * 16 + 2 * k2 * C2P_PLANE) >> 4);
-                        const uint64_t db = desc64(w_lo + (uint32_t)((t * (4 * 64 * 16) + 2 * k2 * 64 * 16) >> 4), W_HI);
-                        tc_mma_bf16(d_tmem, desc64(a_lo + ao, A_HI), db, IDESC64, (t | k2) != 0);
-                        tc_mma_bf16(d_tmem, desc64(a_lo + ao + (uint32_t)((4 * C2P_PLANE) >> 4), A_HI), db, IDESC32, 1);
-                    }
-                }
-                tc_commit(b_aempty + 8 * ab);
-                tc_commit(b_tfull + 8 * acc);
-            }
-        }
-    } else {
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const int trow = q * 4 + (lane >> 3), tcol = lane & 7;        // position inside the 16 x 8 output tile
-        const bool writer = (lane & 9) == 0;                          // even row, even column: owns the pooled pixel
-        for (int i = 0; i < n_my; i++) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-            const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
-            const int acc = i & 1;
-            const long long opix = (long long)patch * 256 + (8 * rb + (trow >> 1)) * 16 + 4 * st + (tcol >> 1);
-            mbar_wait(b_tfull + 8 * acc, (i >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
-#pragma unroll
-            for (int j = half; j < 4; j += 2) {
-                float v[8], u[8];
-                tc_ld8(taddr + 8 * j, v);
-                tc_ld8(taddr + 32 + 8 * j, u);
-                tc_ld_wait();
-                const float4 b0 = __ldg((const float4 *)args.bias + 2 * j), b1 = __ldg((const float4 *)args.bias + 2 * j + 1);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    float x = fmaxf(v[k] + u[k] + bb[k], 0.f);
-                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
-                    v[k] = x;
-                }
-                if (writer) {
-                    uint4 hi, lo;
-                    split8(v, hi, lo);
-                    args.out[(long long)j * args.out_plane + opix] = hi;
-                    args.out[(long long)(4 + j) * args.out_plane + opix] = lo;
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------- elementwise companions
-// conv1 input: per patch pixel the 16-channel row window k = dx*3 + c (dx < 5, c < 3; k = 15 and windows that leave the
-// patch are zero), uint8 -> bf16 (exact). Output planes [chunk 0|1][P*1600 (+pad)][8]. Reads the canonical image in
-// place (NNManager._get_x, nn_manager.py:216-225: 40x40 window at (40 i, 40 j), the last one shifted back to 340).
-__global__ void __launch_bounds__(256) cnn_tc_expand_input(const uint8_t *__restrict__ goban, int n_patches,
-                                                           uint4 *__restrict__ out, long long out_plane)
-{
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n_patches * 1600) return;
-    const int patch = (int)(idx / 1600), rem = (int)(idx % 1600), py = rem / 40, px = rem % 40;
-    const int frame = patch / 100, r = patch % 100;
-    const int x0 = cnn_patch_origin(r / 10), y0 = cnn_patch_origin(r % 10);
-    const uint8_t *src = goban + ((size_t)frame * 380 * 380 + (size_t)(x0 + py) * 380 + y0 + px) * 3;
-    const int nb = min(15, (40 - px) * 3);   // bytes of the window that stay inside the patch row
-    float v[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = k < nb ? (float)__ldg(src + k) : 0.f;
-    uint4 c0, c1;
-    c0.x = pack_bf16x2(v[0], v[1]); c0.y = pack_bf16x2(v[2], v[3]); c0.z = pack_bf16x2(v[4], v[5]); c0.w = pack_bf16x2(v[6], v[7]);
-    c1.x = pack_bf16x2(v[8], v[9]); c1.y = pack_bf16x2(v[10], v[11]); c1.z = pack_bf16x2(v[12], v[13]); c1.w = pack_bf16x2(v[14], v[15]);
-    out[idx] = c0;
-    out[out_plane + idx] = c1;
-}
-
 __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float *v)
 {
     const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -769,15 +488,10 @@ int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
     if (e != cudaSuccess) CKB_FAIL(ctx, CKB_E_CUDA, "tensor-core weight upload failed: %s", cudaGetErrorString(e));
     ctx->cnn->tc_bytes = L.total;
     // opt in to the large dynamic shared memory footprints once
-    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv1Cfg>::SMEM));
-    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv2Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv2Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv3Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv3Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Fc1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Fc1Cfg>::SMEM));
-    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_conv2_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, C2P_SMEM));
-    const char *flat = getenv("CKB_CNN_FLAT_CONV2");
-    ctx->cnn->flat_conv2 = flat && flat[0] == '1';
-    return CKB_OK;
+    return ckb_cnn_front_init(ctx);
 }
 
 void ckb_cnn_tc_free(ckb_ctx *ctx)
@@ -790,34 +504,31 @@ void ckb_cnn_tc_free(ckb_ctx *ctx)
 
 struct TcWork {
     // plane strides in 16-byte units (pixels), each with a tail so that the last tile's halo read stays inside
-    long long x0_plane, a1_plane, a2_plane, p2_plane, a3_plane, a4_plane, p4_plane;
-    size_t x0, a1, a2, p2, a3, a4, p4, f5, tmp, total;
+    long long a1_plane, p2_plane, a3_plane, a4_plane, p4_plane;
+    size_t a1, p2, a3, a4, p4, f5, tmp, total;
 };
 
 static long long plane_units(long long pixels, int halo) { return ((pixels + 127) / 128 * 128 + halo + 7) / 8 * 8; }
 
-static TcWork tc_work_layout(int nf)
+// dump_a1: also reserve room for conv1's activations, which normally never leave shared memory (test aid)
+static TcWork tc_work_layout(int nf, bool dump_a1)
 {
     const long long P = (long long)nf * 100;
     TcWork w;
-    w.x0_plane = plane_units(P * 1600, Derived<Conv1Cfg>::HALO);
-    w.a1_plane = plane_units(P * 1296, Derived<Conv2Cfg>::HALO);
-    w.a2_plane = plane_units(P * 1024, 0);
+    w.a1_plane = dump_a1 ? plane_units(P * 1296, 0) : 0;
     w.p2_plane = plane_units(P * 256, Derived<Conv3Cfg>::HALO);
     w.a3_plane = plane_units(P * 196, Derived<Conv4Cfg>::HALO);
     w.a4_plane = plane_units(P * 144, 0);
     w.p4_plane = plane_units(P, 0);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
-    w.x0 = take((size_t)w.x0_plane * 16 * 2);
-    w.a1 = take((size_t)w.a1_plane * 16 * 8);
-    w.a2 = take((size_t)w.a2_plane * 16 * 8);
     w.p2 = take((size_t)w.p2_plane * 16 * 8);
     w.a3 = take((size_t)w.a3_plane * 16 * 24);
     w.a4 = take((size_t)w.a4_plane * 16 * 24);
     w.p4 = take((size_t)w.p4_plane * 16 * 2 * 36 * 12);
     w.f5 = take((size_t)P * 160 * 4);
     w.tmp = take((size_t)P * (81 + 81 + 2) * 4);
+    w.a1 = take((size_t)w.a1_plane * 16 * 8);
     w.total = o;
     return w;
 }
@@ -825,7 +536,7 @@ static TcWork tc_work_layout(int nf)
 extern "C" size_t ckb_cnn_workspace(const ckb_ctx *ctx, int n)
 {
     if (!ctx || n < 0) return 0;
-    return tc_work_layout(n < TC_MAX_FRAMES ? n : TC_MAX_FRAMES).total + 256;
+    return tc_work_layout(n < TC_MAX_FRAMES ? n : TC_MAX_FRAMES, ctx->cnn && ctx->cnn->dump_a1).total + 256;
 }
 
 template <class L>
@@ -848,50 +559,6 @@ static int launch_layer(ckb_ctx *ctx, const char *name, const void *in, long lon
     return CKB_OK;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// conv2 on 2-D tiles + fused pooling: a1 planes [8][a1_plane] viewed as (8 ch, 36 x, 36*P y, 8 planes)
-static int launch_conv2_pool(ckb_ctx *ctx, const void *a1, long long a1_plane, size_t off_w, size_t off_b, void *p2,
-                             long long p2_plane, int n_patches, cudaStream_t st)
-{
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) CKB_FAIL(ctx, CKB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {8, 36, (cuuint64_t)36 * n_patches, 8};
-    const cuuint64_t gstr[3] = {16, 36 * 16, (cuuint64_t)a1_plane * 16};
-    const cuuint32_t box[4] = {8, 12, 20, 8};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a1), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) CKB_FAIL(ctx, CKB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    Conv2PArgs a;
-    a.w = (const uint4 *)((const uint8_t *)ctx->cnn->d_tc + off_w);
-    a.bias = (const float *)((const uint8_t *)ctx->cnn->d_tc + off_b);
-    a.out = (uint4 *)p2;
-    a.out_plane = p2_plane;
-    a.n_tiles = n_patches * 8;
-    const int grid = a.n_tiles < ctx->num_sms ? a.n_tiles : ctx->num_sms;
-    cnn_tc_conv2_pool<<<grid, TC_THREADS, C2P_SMEM, st>>>(tmap, a);
-    CKB_LAUNCH_CHECK(ctx, "cnn_tc_conv2_pool");
-    return CKB_OK;
-}
-
 #define TC_TRY(call)                 \
     do {                             \
         const int rc__ = (call);     \
@@ -901,25 +568,17 @@ static int launch_conv2_pool(ckb_ctx *ctx, const void *a1, long long a1_plane, s
 static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t *work, float *d_softmax,
                            uint8_t *d_stones, float *d_conf, uint8_t *d_keep, cudaStream_t st)
 {
-    const TcWork W = tc_work_layout(nf);
+    const bool dump = ctx->cnn->dump_a1 != 0;
+    const TcWork W = tc_work_layout(nf, dump);
     const TcBlob B = blob_layout();
     const int P = nf * 100;
-    uint4 *x0 = (uint4 *)(work + W.x0), *a1 = (uint4 *)(work + W.a1), *a2 = (uint4 *)(work + W.a2);
     uint4 *p2 = (uint4 *)(work + W.p2), *a3 = (uint4 *)(work + W.a3), *a4 = (uint4 *)(work + W.a4);
     uint4 *p4 = (uint4 *)(work + W.p4);
     float *f5 = (float *)(work + W.f5);
-    cnn_tc_expand_input<<<(unsigned)(((long long)P * 1600 + 255) / 256), 256, 0, st>>>(d_goban, P, x0, W.x0_plane);
-    CKB_LAUNCH_CHECK(ctx, "cnn_tc_expand_input");
-    TC_TRY(launch_layer<Conv1Cfg>(ctx, "cnn_tc_conv1", x0, W.x0_plane, B.off_w[0], B.off_b[0], a1, W.a1_plane, nullptr,
-                                  (long long)P * 1600, P, st));
-    if (ctx->cnn->flat_conv2) {   // round-1 baseline formulation, kept for A/B measurements (CKB_CNN_FLAT_CONV2=1)
-        TC_TRY(launch_layer<Conv2Cfg>(ctx, "cnn_tc_conv2", a1, W.a1_plane, B.off_w[1], B.off_b[1], a2, W.a2_plane, nullptr,
-                                      (long long)P * 1296, P, st));
-        cnn_tc_pool<32, 4, false><<<(unsigned)(((long long)P * 256 * 4 + 255) / 256), 256, 0, st>>>(a2, W.a2_plane, P, p2, W.p2_plane);
-        CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool2");
-    } else {
-        TC_TRY(launch_conv2_pool(ctx, a1, W.a1_plane, B.off_w[1], B.off_b[1], p2, W.p2_plane, P, st));
-    }
+    const uint8_t *tc = (const uint8_t *)ctx->cnn->d_tc;
+    // gather + conv1 + conv2 + pool in one kernel (cnn_tc_front.cu)
+    TC_TRY(ckb_launch_cnn_front(ctx, d_goban, P, tc + B.off_w[0], (const float *)(tc + B.off_b[0]), tc + B.off_w[1],
+                                (const float *)(tc + B.off_b[1]), p2, W.p2_plane, dump ? work + W.a1 : nullptr, W.a1_plane, st));
     TC_TRY(launch_layer<Conv3Cfg>(ctx, "cnn_tc_conv3", p2, W.p2_plane, B.off_w[2], B.off_b[2], a3, W.a3_plane, nullptr,
                                   (long long)P * 256, P, st));
     TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
@@ -951,13 +610,23 @@ extern "C" int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void
     return CKB_OK;
 }
 
+// Test aid: keep conv1's activations (which normally live only in shared memory) in the workspace during the next
+// forward passes, so that ckb_cnn_debug_activation(layer 1) can return them. Changes ckb_cnn_workspace().
+extern "C" int ckb_cnn_set_debug(ckb_ctx *ctx, int on)
+{
+    if (!ctx || !ctx->cnn) return CKB_E_INVALID;
+    ctx->cnn->dump_a1 = on != 0;
+    return CKB_OK;
+}
+
 // Test aid: after ckb_cnn_forward on n <= 64 frames, unpack one intermediate activation of the tensor-core path from
 // the workspace into dense float32 [patch][H][W][C]: layer 1 = conv1 (36,36,32), 2 = pooled conv2 (16,16,32),
 // 3 = conv3 (14,14,90), 4 = pooled conv4 (6,6,90; from fc1's tap planes), 5 = fc1 (160).
 extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n, int layer, float *d_out, void *stream)
 {
     if (!ctx || !d_work || !d_out || n < 1 || n > TC_MAX_FRAMES) return CKB_E_INVALID;
-    const TcWork W = tc_work_layout(n);
+    const bool dump = ctx->cnn && ctx->cnn->dump_a1;
+    const TcWork W = tc_work_layout(n, dump);
     const uint8_t *work = (const uint8_t *)d_work;
     cudaStream_t st = (cudaStream_t)stream;
     CKB_ENTER(ctx, stream);
@@ -966,7 +635,10 @@ extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n,
         cnn_tc_unpack<<<(unsigned)((npix * KC + 255) / 256), 256, 0, st>>>((const uint4 *)(work + off), plane, KC, npix, C, d_out);
     };
     switch (layer) {
-    case 1: go(W.a1, W.a1_plane, 4, P * 1296, 32); break;
+    case 1:
+        if (!dump) CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_debug_activation: layer 1 needs ckb_cnn_set_debug(ctx, 1) before the forward pass");
+        go(W.a1, W.a1_plane, 4, P * 1296, 32);
+        break;
     case 2: go(W.p2, W.p2_plane, 4, P * 256, 32); break;
     case 3: go(W.a3, W.a3_plane, 12, P * 196, 90); break;
     case 5: CKB_CUDA(ctx, cudaMemcpyAsync(d_out, work + W.f5, (size_t)P * 160 * 4, cudaMemcpyDeviceToDevice, st)); return CKB_OK;

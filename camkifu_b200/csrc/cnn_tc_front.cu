@@ -1,0 +1,309 @@
+// K4 front end: patch gather + conv1 + ReLU + conv2 + ReLU + 2x2 max-pool of the SfNeural CNN in ONE tcgen05 kernel.
+//
+// Replaces NNManager._get_x (nn_manager.py:216-225) and the first four layers of NNManager.create_net
+// (nn_manager.py:280-285: Convolution2D(32,5,5) relu, Convolution2D(32,5,5) relu, MaxPooling2D(2,2)). conv2 is half of
+// the network's MACs and conv1's 36x36x32 output is its largest activation (166 KB per patch as bf16 hi/lo planes,
+// 1.06 GB per 64 frames): computing conv1 per conv2 tile inside the same kernel keeps that activation in shared memory
+// and removes the separate gather/expand and conv1 kernels, which were HBM-bound.
+//
+// One tile = 8 (x) by 16 (y) conv2 outputs of one patch. Per tile, with everything double buffered:
+//   workers  : read the 24 x 16 raw uint8 window of the canonical image and expand it to conv1's A operand X
+//              (per pixel the 5-pixel row window, k = dx*3 + c, 16 bf16 = two 16-byte chunks)          -> smem X
+//   tensor   : conv1 = 5 vertical taps, 2 M-tiles of 128 window pixels, B = [W1_hi | W1_lo] (N = 64)   -> TMEM D1
+//   workers  : D1 -> +bias, ReLU, bf16 hi/lo split -> conv2's A tile [plane][row 20][12 px][16 B]      -> smem A
+//   tensor   : conv2 = 25 taps x 2 K-steps x (A_hi [W_hi | W_lo] N = 64, A_lo W_hi N = 32); the tap shift is a start
+//              address offset of the A descriptor, SBO = the window's row pitch                         -> TMEM D2
+//   workers  : D2 -> +bias, ReLU, 2x2 max by warp shuffles, hi/lo split -> pooled planes in HBM (conv3's input)
+// Warp 0 issues all MMAs (one elected thread); warps 1-8 are the workers (two per TMEM lane quarter).
+// Precision: bf16 hi/lo operand split, fp32 accumulation; conv1's uint8 input is exact in bf16.
+#include <cuda_bf16.h>
+
+#include "cnn_common.cuh"
+#include "tc_ptx.cuh"
+
+#define FR_WORKERS 8
+#define FR_THREADS (32 + 32 * FR_WORKERS)
+
+#define FR_XROWS 304                          // 24 x 12 window pixels + tail read by the last M-tile's taps
+#define FR_XPLANE (FR_XROWS * 16)             // 4864 B per 8-channel chunk
+#define FR_XTILE (2 * FR_XPLANE)              // 9728 B
+#define FR_ROWPITCH 192                       // conv2 A tile: 12 pixels x 16 B
+#define FR_APLANE (20 * FR_ROWPITCH)          // 3840 B
+#define FR_ATILE (8 * FR_APLANE)              // 30720 B: 4 chunks x (hi, lo)
+#define FR_W1 (5 * 2 * 64 * 16)               // 10240 B  [dy][chunk][W_hi | W_lo rows][8]
+#define FR_W2 (25 * 4 * 64 * 16)              // 102400 B [tap][chunk][W_hi | W_lo rows][8]
+#define FR_SMEM (2 * FR_XTILE + 2 * FR_ATILE + FR_W1 + FR_W2 + 256 + 128)
+
+struct FrontArgs {
+    const uint8_t *goban;   // canonical images [frames][380][380][3]
+    const uint4 *w1, *w2;   // packed operand planes (cnn_tc.cu: pack_layer<Conv1Cfg>, <Conv2Cfg>)
+    const float *b1, *b2;
+    uint4 *out;             // pooled planes [2][4][out_plane], pixel = patch*256 + y*16 + x
+    long long out_plane;
+    uint4 *dbg_a1;          // optional: conv1 activations [2][4][a1_plane], pixel = patch*1296 + y*36 + x (tests)
+    long long a1_plane;
+    int n_tiles;            // patches * 8
+};
+
+__global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_constant__ FrontArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *sX = smem;
+    uint8_t *sA = sX + 2 * FR_XTILE;
+    uint8_t *sW1 = sA + 2 * FR_ATILE;
+    uint8_t *sW2 = sW1 + FR_W1;
+    uint64_t *bars = (uint64_t *)(sW2 + FR_W2);
+    const uint32_t b_xfull = smem_u32(bars + 0), b_xempty = smem_u32(bars + 2), b_d1full = smem_u32(bars + 4),
+                   b_d1empty = smem_u32(bars + 6), b_afull = smem_u32(bars + 8), b_aempty = smem_u32(bars + 10),
+                   b_d2full = smem_u32(bars + 12), b_d2empty = smem_u32(bars + 14), b_wfull = smem_u32(bars + 16);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 17);
+    const int warp = warp_index(), lane = threadIdx.x & 31;
+    const int n_my = (args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(b_xfull + 8 * i, FR_WORKERS);  mbar_init(b_xempty + 8 * i, 1);
+            mbar_init(b_d1full + 8 * i, 1);          mbar_init(b_d1empty + 8 * i, FR_WORKERS);
+            mbar_init(b_afull + 8 * i, FR_WORKERS);  mbar_init(b_aempty + 8 * i, 1);
+            mbar_init(b_d2full + 8 * i, 1);          mbar_init(b_d2empty + 8 * i, FR_WORKERS);
+        }
+        mbar_init(b_wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the tail rows of X are read (rows of discarded outputs) but never written by the workers: keep them finite
+    for (int i = threadIdx.x; i < 2 * FR_XTILE / 16; i += FR_THREADS) ((uint4 *)sX)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: D2 accumulators [0, 128) = 2 x 64; D1 accumulators [128, 384) = 2 buffers x 2 M-tiles x 64
+    constexpr uint32_t D1_COL = 128;
+
+    if (warp == 0) {
+        // ================================================================= MMA issuer (+ one-off weight load by TMA)
+        if (elect_one()) {
+            mbar_expect_tx(b_wfull, FR_W1 + FR_W2);
+            bulk_g2s(smem_u32(sW1), args.w1, FR_W1, b_wfull);
+            for (int off = 0; off < FR_W2; off += 25600) bulk_g2s(smem_u32(sW2 + off), (const uint8_t *)args.w2 + off, 25600, b_wfull);
+            constexpr uint32_t IDESC64 = umma_idesc(64), IDESC32 = umma_idesc(32);
+            constexpr uint32_t HI128 = desc_hi(128), HI_A = desc_hi(FR_ROWPITCH);
+            const uint32_t w1_lo = desc_lo(smem_u32(sW1), 64 * 16), w2_lo = desc_lo(smem_u32(sW2), 64 * 16);
+            mbar_wait(b_wfull, 0);
+
+            auto conv1 = [&](int i) {
+                const int b = i & 1, k = i >> 1;
+                mbar_wait(b_xfull + 8 * b, k & 1);
+                mbar_wait(b_d1empty + 8 * b, (k & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t x_lo = desc_lo(smem_u32(sX + b * FR_XTILE), FR_XPLANE);
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int dy = 0; dy < 5; dy++)
+                        tc_mma_bf16(tmem_base + D1_COL + b * 128 + mt * 64, desc64(x_lo + (uint32_t)(mt * 128 + dy * 12), HI128),
+                                    desc64(w1_lo + (uint32_t)((dy * 2 * 64 * 16) >> 4), HI128), IDESC64, dy != 0);
+                tc_commit(b_xempty + 8 * b);
+                tc_commit(b_d1full + 8 * b);
+            };
+
+            conv1(0);
+            for (int i = 0; i < n_my; i++) {
+                if (i + 1 < n_my) conv1(i + 1);
+                const int b = i & 1, k = i >> 1;
+                mbar_wait(b_afull + 8 * b, k & 1);
+                mbar_wait(b_d2empty + 8 * b, (k & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + b * 64;
+                const uint32_t a_lo = desc_lo(smem_u32(sA + b * FR_ATILE), FR_APLANE);
+#pragma unroll
+                for (int t = 0; t < 25; t++) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; k2++) {
+                        const uint32_t ao = (uint32_t)((((t / 5) * 12 + (t % 5)) * 16 + 2 * k2 * FR_APLANE) >> 4);
+                        const uint64_t db = desc64(w2_lo + (uint32_t)((t * (4 * 64 * 16) + 2 * k2 * 64 * 16) >> 4), HI128);
+                        tc_mma_bf16(d_tmem, desc64(a_lo + ao, HI_A), db, IDESC64, (t | k2) != 0);
+                        tc_mma_bf16(d_tmem, desc64(a_lo + ao + (uint32_t)((4 * FR_APLANE) >> 4), HI_A), db, IDESC32, 1);
+                    }
+                }
+                tc_commit(b_aempty + 8 * b);
+                tc_commit(b_d2full + 8 * b);
+            }
+        }
+    } else {
+        // ============================================================================================== workers
+        const int wt = threadIdx.x - 32;                     // 0..255
+        const int q = warp & 3, half = (warp - 1) >> 2;      // TMEM lane quarter of this warp; which channel chunks
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        // ---- X: raw uint8 window -> conv1 operand rows. Window pixel (ry, rx), ry < 24, rx < 12 -> row ry*12 + rx
+        auto build_x = [&](int i) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
+            const int frame = patch / 100, r = patch % 100;
+            const int row0 = cnn_patch_origin(r / 10) + 16 * rb, col0 = cnn_patch_origin(r % 10) + 8 * st;
+            const uint8_t *base = args.goban + (size_t)frame * (380 * 380 * 3);
+            uint8_t *xt = sX + (i & 1) * FR_XTILE;
+            for (int idx = wt; idx < 288; idx += 32 * FR_WORKERS) {
+                const int ry = idx / 12, rx = idx - ry * 12;
+                const uint8_t *src = base + ((size_t)(row0 + ry) * 380 + col0 + rx) * 3;   // 15 bytes: 5 px x BGR
+                const uintptr_t a = (uintptr_t)src;
+                const uint32_t *wp = (const uint32_t *)(a & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(a & 3) * 8;
+                uint32_t w[5];
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = __ldg(wp + j);
+                w[4] = sh >= 16 ? __ldg(wp + 4) : 0u;      // only misalignments 2, 3 need a 5th word
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = __funnelshift_r(w[j], w[j + 1], sh);
+                v[3] &= 0x00ffffffu;                        // k = 15 is padding
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    o[2 * j] = pack_bf16x2((float)(v[j] & 0xff), (float)((v[j] >> 8) & 0xff));
+                    o[2 * j + 1] = pack_bf16x2((float)((v[j] >> 16) & 0xff), (float)(v[j] >> 24));
+                }
+                *(uint4 *)(xt + idx * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                *(uint4 *)(xt + FR_XPLANE + idx * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_xfull + 8 * (i & 1));
+        };
+
+        // ---- epilogue 1: D1 (conv1 accumulators) -> bias, ReLU, hi/lo split -> conv2's A tile in shared memory
+        auto epilogue1 = [&](int i) {
+            const int b = i & 1, k = i >> 1;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            mbar_wait(b_d1full + 8 * b, k & 1);
+            mbar_wait(b_aempty + 8 * b, (k & 1) ^ 1);
+            tc_fence_after();
+            uint8_t *at = sA + b * FR_ATILE;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const int m = mt * 128 + q * 32 + lane;      // window pixel (wy, wx) = (m / 12, m % 12), 240 valid
+                const int wy = m / 12, wx = m - wy * 12;
+                const uint32_t taddr = lane_base + D1_COL + b * 128 + mt * 64;
+#pragma unroll
+                for (int c2 = 0; c2 < 2; c2++) {
+                    const int cc = 2 * half + c2;
+                    float v[8], u[8];
+                    tc_ld8(taddr + 8 * cc, v);
+                    tc_ld8(taddr + 32 + 8 * cc, u);
+                    tc_ld_wait();
+                    const float4 b0 = __ldg((const float4 *)args.b1 + 2 * cc), b1 = __ldg((const float4 *)args.b1 + 2 * cc + 1);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j] + u[j] + bb[j], 0.f);
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    if (m < 240) {
+                        *(uint4 *)(at + cc * FR_APLANE + m * 16) = hi;          // wy * 192 + wx * 16 == m * 16
+                        *(uint4 *)(at + (4 + cc) * FR_APLANE + m * 16) = lo;
+                        if (args.dbg_a1) {
+                            const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
+                            const long long p = (long long)patch * 1296 + (16 * rb + wy) * 36 + 8 * st + wx;
+                            args.dbg_a1[(long long)cc * args.a1_plane + p] = hi;
+                            args.dbg_a1[(long long)(4 + cc) * args.a1_plane + p] = lo;
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(b_afull + 8 * b);
+                mbar_arrive(b_d1empty + 8 * b);
+            }
+        };
+
+        // ---- epilogue 2: D2 (conv2 accumulators) -> bias, ReLU, 2x2 max-pool, hi/lo split -> HBM
+        // MMA row m = 8 * (tile row) + (tile column): the pooling window of an even (row, column) is lanes l, l+1, l+8, l+9
+        auto epilogue2 = [&](int i) {
+            const int b = i & 1, k = i >> 1;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int patch = tile >> 3, rb = (tile >> 2) & 1, st = tile & 3;
+            const int trow = q * 4 + (lane >> 3), tcol = lane & 7;
+            const bool writer = (lane & 9) == 0;
+            const long long opix = (long long)patch * 256 + (8 * rb + (trow >> 1)) * 16 + 4 * st + (tcol >> 1);
+            mbar_wait(b_d2full + 8 * b, k & 1);
+            tc_fence_after();
+            const uint32_t taddr = lane_base + b * 64;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const int cc = 2 * half + c2;
+                float v[8], u[8];
+                tc_ld8(taddr + 8 * cc, v);
+                tc_ld8(taddr + 32 + 8 * cc, u);
+                tc_ld_wait();
+                const float4 b0 = __ldg((const float4 *)args.b2 + 2 * cc), b1 = __ldg((const float4 *)args.b2 + 2 * cc + 1);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float x = fmaxf(v[j] + u[j] + bb[j], 0.f);
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                    v[j] = x;
+                }
+                if (writer) {
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    args.out[(long long)cc * args.out_plane + opix] = hi;
+                    args.out[(long long)(4 + cc) * args.out_plane + opix] = lo;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_d2empty + 8 * b);
+        };
+
+        build_x(0);
+        if (n_my > 1) build_x(1);
+        for (int i = 0; i < n_my; i++) {
+            epilogue1(i);
+            if (i + 2 < n_my) {
+                mbar_wait(b_xempty + 8 * (i & 1), (i >> 1) & 1);   // conv1(i) has consumed this X buffer
+                build_x(i + 2);
+            }
+            if (i >= 1) epilogue2(i - 1);
+        }
+        epilogue2(n_my - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+int ckb_cnn_front_init(ckb_ctx *ctx)
+{
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_front, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM));
+    return CKB_OK;
+}
+
+int ckb_launch_cnn_front(ckb_ctx *ctx, const uint8_t *d_goban, int n_patches, const void *w1, const float *b1, const void *w2,
+                         const float *b2, void *p2, long long p2_plane, void *dbg_a1, long long a1_plane, cudaStream_t st)
+{
+    FrontArgs a;
+    a.goban = d_goban;
+    a.w1 = (const uint4 *)w1;
+    a.w2 = (const uint4 *)w2;
+    a.b1 = b1;
+    a.b2 = b2;
+    a.out = (uint4 *)p2;
+    a.out_plane = p2_plane;
+    a.dbg_a1 = (uint4 *)dbg_a1;
+    a.a1_plane = a1_plane;
+    a.n_tiles = n_patches * 8;
+    const int grid = a.n_tiles < ctx->num_sms ? a.n_tiles : ctx->num_sms;
+    cnn_tc_front<<<grid, FR_THREADS, FR_SMEM, st>>>(a);
+    CKB_LAUNCH_CHECK(ctx, "cnn_tc_front");
+    return CKB_OK;
+}

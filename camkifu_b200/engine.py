@@ -176,6 +176,10 @@ class StoneEngine:
                        self._ptr(out["stones"]), self._ptr(out["conf"]), self._ptr(out["keep"]), self._stream()))
         return out
 
+    def cnn_set_debug(self, on: bool):
+        """Test aid: keep conv1's activations in the workspace during the following cnn_forward calls."""
+        self._check(self.L.ckb_cnn_set_debug(self._h, int(bool(on))))
+
     def cnn_debug_activation(self, n: int, layer: int) -> torch.Tensor:
         """Test aid: dense float32 copy of an intermediate activation of the last cnn_forward (n <= 64 frames)."""
         shape = {1: (36, 36, 32), 2: (16, 16, 32), 3: (14, 14, 90), 5: (160,)}[layer]

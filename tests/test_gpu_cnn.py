@@ -64,20 +64,24 @@ def test_tc_layers_vs_oracle(engine, oracle):
     relative to the layer's largest activation the error must stay below 1e-4."""
     goban = boards(1, seed=5)
     params = weights.glorot_params(seed=0, bias_scale=0.5)
-    engine.cnn_forward(torch.from_numpy(goban).cuda())
     xs = oracle.c_nn_gather(goban[0])
     y, acts = oracle.c_cnn_forward(xs, params, want_acts=True)
     sizes = [("conv1", 1, 36 * 36 * 32), ("pool2", 2, 16 * 16 * 32), ("conv3", 3, 14 * 14 * 90), ("pool4", None, 3240),
              ("fc1", 5, 160)]
-    off = 0
-    for name, layer, sz in sizes:
-        ref = acts[:, off:off + sz]
-        off += sz
-        if layer is None:
-            continue
-        got = engine.cnn_debug_activation(1, layer).cpu().numpy().reshape(100, -1)
-        err = np.abs(got - ref).max() / np.abs(ref).max()
-        assert err < 1e-4, "%s: relative error %.3g" % (name, err)
+    engine.cnn_set_debug(True)      # conv1's activations normally stay in shared memory (fused front kernel)
+    try:
+        engine.cnn_forward(torch.from_numpy(goban).cuda())
+        off = 0
+        for name, layer, sz in sizes:
+            ref = acts[:, off:off + sz]
+            off += sz
+            if layer is None:
+                continue
+            got = engine.cnn_debug_activation(1, layer).cpu().numpy().reshape(100, -1)
+            err = np.abs(got - ref).max() / np.abs(ref).max()
+            assert err < 1e-4, "%s: relative error %.3g" % (name, err)
+    finally:
+        engine.cnn_set_debug(False)
 
 
 @pytest.mark.parametrize("n", [1, 3])
