@@ -10,8 +10,8 @@ Workload (config.workload): BASELINE.json configs[1] — SfNeural CNN stone clas
 of the reference architecture: the trained weights do not ship with the reference.
 
 `value`   frames/s with the frames resident in HBM, CUDA events on the launching stream, max over ranks.
-`e2e`     the same metric through camkifu_b200.pipeline.DetectPipeline.detect() with HOST (pinned) frames: H2D of the
-          frames and D2H of the board states inside the timed region.
+`e2e`     the same metric through camkifu_b200.pipeline.DetectPipeline.detect_stream() with HOST (pinned) frames: H2D of
+          the frames and D2H of the board states inside the timed region (batch k+1 uploads while batch k computes).
 `roofline` dominant kernel = cnn_tc_front (patch gather + conv1 + conv2 + pool on tcgen05); achieved = algorithmic FLOP / mean launch time measured with
           CUDA events in the timed region (ckb_profile_begin/end); peak from MEASURED_PEAKS.json.
 `cpu_baseline` the reference's CPU path (cv2 warp + fp32 CNN, oracle/) on a bounded sample, timed on this host.
@@ -40,7 +40,7 @@ CNN_MAC_PER_PATCH = {"conv1": 36 * 36 * 75 * 32, "conv2": 32 * 32 * 800 * 32, "c
 assert sum(CNN_MAC_PER_PATCH.values()) == 45434080
 # dram__bytes_read.sum + dram__bytes_write.sum of one cnn_tc_front launch (64 frames), from the ncu --set full capture
 # committed under profiles/ (None until a capture exists for the current kernel)
-FRONT_DRAM_TRAFFIC_BYTES = None
+FRONT_DRAM_TRAFFIC_BYTES = 27915776 + 156647424   # profiles/r1c_cnn_tc_kernels_ncu_full_selected.csv
 
 
 def measured_peaks():
@@ -231,8 +231,9 @@ def run_b200(args, rank, world, local_rank):
     e2e_steps = args.steps
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(e2e_steps):
-        res = pipe.detect(host, mtx)     # returns after the D2H of the board states (synchronous API)
+    # offline-video form of the API: batch k+1 uploads while batch k computes; every result is read back on the host
+    for res in pipe.detect_stream(((host, mtx) for _ in range(e2e_steps)), depth=2):
+        pass
     f1.record()
     barrier()
     e2e_s = f0.elapsed_time(f1) / 1e3
@@ -286,8 +287,8 @@ def run_b200(args, rank, world, local_rank):
                        "l2": "inputs larger than L2: two resident 398 MB batches used alternately",
                        "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "camkifu_b200.pipeline.DetectPipeline.detect (pinned host frames, ROI upload, 16-frame "
-                           "sub-batches double buffered)", "matches_resident_path": e2e_ok},
+                    "api": "camkifu_b200.pipeline.DetectPipeline.detect_stream (pinned host frames, ROI upload, 16-frame "
+                           "sub-batches double buffered, results of every batch read back to the host)", "matches_resident_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d frames of the same clip: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "

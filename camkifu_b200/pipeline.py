@@ -40,42 +40,61 @@ class DetectPipeline:
         self.comp_stream = torch.cuda.Stream(device=dev)
         self.ev_up = [torch.cuda.Event() for _ in range(2)]
         self.ev_free = [torch.cuda.Event() for _ in range(2)]
-        self._cap = 0
+        self._k = 0                     # sub-batches enqueued so far (the device frame buffers are a ring of two)
+        self._slots = []                # output slots (pinned host buffers + completion event), a ring of DEPTH
+        self._ticket = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _ensure_out(self, n):
-        if n <= self._cap:
-            return
-        g = self.eng.gsize
-        self.out = {}
-        if self.mode != "clustering":
-            self.out["stones"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
-            self.out["keep"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
-            self.out["conf"] = torch.empty((n, g, g), dtype=torch.float32, pin_memory=True)
-        if self.mode != "neural":
-            self.out["km_stones"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
-            self.out["km_trusted"] = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
-        self._cap = n
+    DEPTH = 3   # batches that may be in flight (submit() without collect())
 
-    def detect(self, frames: torch.Tensor, mtx, rng_state: int = None, crop: bool = True):
-        """frames: HOST uint8 [n, H, W, 3] (torch tensor, ideally pinned; numpy arrays are wrapped), mtx: the 3x3
-        frame -> canonical homography of the segment. rng_state: cv::RNG state before the first k-means call
-        (clustering modes; defaults to cv2.setRNGSeed(0)'s). Returns {name: numpy array [n, ...]}."""
+    def _slot(self, ticket, n):
+        g = self.eng.gsize
+        while len(self._slots) < self.DEPTH:
+            self._slots.append({"cap": 0, "out": {}, "done": torch.cuda.Event(), "ticket": -1, "n": 0})
+        sl = self._slots[ticket % self.DEPTH]
+        if sl["ticket"] >= 0 and sl["ticket"] != ticket:
+            sl["done"].synchronize()    # the slot's previous batch must have been produced before it is reused
+        if n > sl["cap"]:
+            out = {}
+            if self.mode != "clustering":
+                out["stones"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
+                out["keep"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
+                out["conf"] = torch.empty((n, g, g), dtype=torch.float32, pin_memory=True)
+            if self.mode != "neural":
+                out["km_stones"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
+                out["km_trusted"] = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+            sl["out"], sl["cap"] = out, n
+        sl["ticket"], sl["n"] = ticket, n
+        return sl
+
+    def submit(self, frames: torch.Tensor, mtx, rng_state: int = None, crop: bool = True) -> int:
+        """Enqueue one batch: frames HOST uint8 [n, H, W, 3] (torch tensor, ideally pinned; numpy arrays are wrapped),
+        mtx the 3x3 frame -> canonical homography of the segment, rng_state the cv::RNG state before the first k-means
+        call (clustering modes; defaults to cv2.setRNGSeed(0)'s). Returns a ticket for collect(). The call only
+        enqueues copies and kernels: the upload of this batch overlaps the kernels of the previous one. `frames` must
+        stay untouched until the batch is collected; at most DEPTH batches may be outstanding."""
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         n = frames.shape[0]
         assert tuple(frames.shape[1:]) == (self.H, self.W, 3)
-        self._ensure_out(n)
+        ticket = self._ticket
+        self._ticket += 1
+        sl = self._slot(ticket, n)
+        out = sl["out"]
         eng = self.eng
         roi = eng.frame_roi(mtx, self.H, self.W) if crop else None
         st0 = rng_seed(0) if rng_state is None else rng_state
         self.h2d_bytes = self.d2h_bytes = 0
-        cur = torch.cuda.current_stream(eng.device)
-        self.copy_stream.wait_stream(cur)
-        self.comp_stream.wait_stream(cur)
-        for k, f0 in enumerate(range(0, n, self.sub)):
+        if ticket == 0 or self._idle:
+            cur = torch.cuda.current_stream(eng.device)
+            self.copy_stream.wait_stream(cur)
+            self.comp_stream.wait_stream(cur)
+            self._idle = False
+        for f0 in range(0, n, self.sub):
             m = min(self.sub, n - f0)
+            k = self._k
+            self._k += 1
             b = k & 1
             with torch.cuda.stream(self.copy_stream):
                 if k >= 2:
@@ -89,15 +108,44 @@ class DetectPipeline:
                 if self.mode != "clustering":
                     r = eng.cnn_forward(goban, want_softmax=False)
                     for name in ("stones", "keep", "conf"):
-                        self.out[name][f0:f0 + m].copy_(r[name], non_blocking=True)
+                        out[name][f0:f0 + m].copy_(r[name], non_blocking=True)
                         self.d2h_bytes += r[name].numel() * r[name].element_size()
                 if self.mode != "neural":
                     states = [rng_advance(st0, f0 + i) for i in range(m)]
                     r = eng.find_stones(goban, states)
-                    self.out["km_stones"][f0:f0 + m].copy_(r["stones"], non_blocking=True)
-                    self.out["km_trusted"][f0:f0 + m].copy_(r["trusted"], non_blocking=True)
+                    out["km_stones"][f0:f0 + m].copy_(r["stones"], non_blocking=True)
+                    out["km_trusted"][f0:f0 + m].copy_(r["trusted"], non_blocking=True)
                     self.d2h_bytes += r["stones"].numel() + r["trusted"].numel()
+        sl["done"].record(self.comp_stream)
+        return ticket
+
+    _idle = True
+
+    def collect(self, ticket: int):
+        """Wait for a submitted batch; returns {name: numpy array [n, ...]} (views of pinned host buffers, valid until
+        DEPTH more batches have been submitted)."""
+        sl = self._slots[ticket % self.DEPTH]
+        if sl["ticket"] != ticket:
+            raise ValueError("ticket %d is no longer available (at most %d batches may be outstanding)" % (ticket, self.DEPTH))
+        sl["done"].synchronize()
+        return {k: v[:sl["n"]].numpy() for k, v in sl["out"].items()}
+
+    def detect(self, frames: torch.Tensor, mtx, rng_state: int = None, crop: bool = True):
+        """Synchronous form: submit + collect of one batch (see submit)."""
+        res = self.collect(self.submit(frames, mtx, rng_state, crop))
+        cur = torch.cuda.current_stream(self.eng.device)
         cur.wait_stream(self.comp_stream)
-        cur.wait_stream(self.copy_stream)
-        cur.synchronize()
-        return {k: v[:n].numpy() for k, v in self.out.items()}
+        self._idle = True
+        return res
+
+    def detect_stream(self, batches, depth: int = 2):
+        """Offline video: `batches` yields (frames, mtx) or (frames, mtx, rng_state); results are yielded in order while
+        up to `depth` (<= DEPTH - 1) later batches are already uploading / computing."""
+        depth = max(1, min(depth, self.DEPTH - 1))
+        pending = []
+        for item in batches:
+            pending.append(self.submit(*item))
+            if len(pending) > depth:
+                yield self.collect(pending.pop(0))
+        while pending:
+            yield self.collect(pending.pop(0))

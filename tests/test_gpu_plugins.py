@@ -115,3 +115,29 @@ def test_detect_pipeline_matches_engine(oracle):
     assert np.array_equal(res["km_stones"], truth)   # the k-means path reads these synthetic boards perfectly
     g0 = goban[0].cpu().numpy()
     assert np.array_equal(g0, oracle.c_warp(frames[0], mtx, 380))
+
+
+def test_detect_stream_matches_synchronous_calls():
+    """submit/collect pipelining (batch k+1 uploads while batch k computes) returns the same board states, in order,
+    as one synchronous detect() per batch; different segments (homographies) may follow each other."""
+    from camkifu_b200.pipeline import DetectPipeline, pinned_frames
+    H, W = 360, 480
+    params = weights.glorot_params(seed=0)
+    pipe = DetectPipeline(H, W, mode="neural", sub_batch=4, cnn_params=params)
+    batches = []
+    for seed, n in ((4, 9), (5, 4), (6, 13), (7, 1), (8, 8)):
+        frames, mtx, _, _ = synth.make_clip(seed, n, H, W)
+        host = pinned_frames(n, H, W)
+        host.copy_(torch.from_numpy(frames))
+        batches.append((host, mtx))
+    sync = [{k: v.copy() for k, v in pipe.detect(h, m).items()} for h, m in batches]
+    got = [{k: v.copy() for k, v in r.items()} for r in pipe.detect_stream(iter(batches), depth=2)]
+    assert len(got) == len(sync)
+    for a, b in zip(got, sync):
+        for k in b:
+            assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(ValueError):
+        t0 = pipe.submit(*batches[0])
+        for h, m in batches[1:4]:
+            pipe.submit(h, m)
+        pipe.collect(t0)           # its slot has been reused: at most DEPTH batches may be outstanding
