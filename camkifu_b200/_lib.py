@@ -27,6 +27,10 @@ SIGNATURES = {
                            C.c_void_p]),
     "ckb_accumulate": (C.c_int, [C.c_void_p, _u8p, C.c_int, _f32p, C.c_float, C.c_int, _f32p, C.c_int, C.c_int,
                                  C.c_void_p]),
+    "ckb_mog2_state_bytes": (C.c_size_t, [C.c_void_p]),
+    "ckb_mog2_reset": (C.c_int, [C.c_void_p, _vp, C.c_void_p]),
+    "ckb_mog2_apply": (C.c_int, [C.c_void_p, _u8p, C.c_int, _vp, C.c_longlong, C.c_void_p, _u8p, C.c_void_p]),
+    "ckb_zone_fg_counts": (C.c_int, [C.c_void_p, _u8p, C.c_int, _vp, C.c_void_p]),
     "ckb_find_stones_workspace": (C.c_size_t, [C.c_void_p, C.c_int]),
     "ckb_find_stones": (C.c_int, [C.c_void_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _vp,
                                   C.c_size_t, _u8p, _u8p, _u8p, _f32p, _f64p, _i32p, C.c_void_p]),

@@ -113,6 +113,37 @@ class StoneEngine:
                                           self._ptr(snaps), max(snap_every, 1), snap_phase, self._stream()))
         return snaps
 
+    # ---------------------------------------------------------------------------------------------- background model
+    def mog2_new_state(self) -> torch.Tensor:
+        """Device state of a fresh cv2.createBackgroundSubtractorMOG2(detectShadows=False) (stonesfinder.py:113-115)."""
+        st = torch.empty(int(self.L.ckb_mog2_state_bytes(self._h)), dtype=torch.uint8, device=self.device)
+        self._check(self.L.ckb_mog2_reset(self._h, self._ptr(st), self._stream()))
+        return st
+
+    def mog2_apply(self, goban: torch.Tensor, state: torch.Tensor, frames_before: int, learning_rates, out=None):
+        """bg_model.apply(goban_img, learningRate=lr) for n canonical images in order (stonesfinder.py:171-176).
+        frames_before: frames this model has already seen. Returns the foreground masks uint8 [n, S, S] (0 / 255)."""
+        if goban.dim() == 3:
+            goban = goban.unsqueeze(0)
+        n = goban.shape[0]
+        assert goban.is_contiguous() and goban.dtype == torch.uint8 and goban.shape[1:] == (self.S, self.S, 3)
+        lr = np.ascontiguousarray(np.broadcast_to(np.asarray(learning_rates, dtype=np.float64), (n,)))
+        if out is None:
+            out = torch.empty((n, self.S, self.S), dtype=torch.uint8, device=self.device)
+        self._check(self.L.ckb_mog2_apply(self._h, self._ptr(goban), n, self._ptr(state), int(frames_before),
+                                          lr.ctypes.data_as(C.c_void_p), self._ptr(out), self._stream()))
+        return out
+
+    def zone_fg_counts(self, fgmask: torch.Tensor) -> torch.Tensor:
+        """Foreground pixels per zone rectangle, int32 [n, g, g] (= np.sum(fg[a0:a1, b0:b1]) / 255, sf_neural.py:178-180)."""
+        if fgmask.dim() == 2:
+            fgmask = fgmask.unsqueeze(0)
+        n = fgmask.shape[0]
+        assert fgmask.is_contiguous() and fgmask.dtype == torch.uint8 and fgmask.shape[1:] == (self.S, self.S)
+        out = torch.empty((n, self.gsize, self.gsize), dtype=torch.int32, device=self.device)
+        self._check(self.L.ckb_zone_fg_counts(self._h, self._ptr(fgmask), n, self._ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------------------------------------------------------------- K3 + K2
     def find_stones(self, imgs: torch.Tensor, rng_states, rs=0, re=None, cs=0, ce=None, want=("stones", "trusted")):
         """SfClustering.find_stones on n canonical images (uint8 or float32 [n, S, S, 3]).

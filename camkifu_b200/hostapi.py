@@ -84,7 +84,7 @@ class StonesFinderBase:
         raise NotImplementedError("Abstract method meant to be extended")
 
     def _learn_bg(self):
-        pass   # MOG2 background model: SURVEY.md section 8(f1), not on the path built here
+        pass   # the B200 plugins keep the MOG2 background model on the device (plugins._DeviceFrames._learn_bg)
 
     def _learn(self):
         pass

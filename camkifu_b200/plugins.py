@@ -11,8 +11,10 @@ Both keep the reference's plugin contract: constructor `(
 
 The warp lives in the base `_doframe` (stonesfinder.py:140), so `_doframe` is overridden: the frame goes to the device,
 `ckb_warp` produces the canonical image there, `self.goban_img` is kept as the host copy other code reads
-(vmanager.py:310-321), and detection runs on the device-resident image. There is no CPU fallback: without the CUDA
-library or a GPU the first frame raises.
+(vmanager.py:310-321), and detection runs on the device-resident image. Finders that ask for a background model
+(`learn_bg`, stonesfinder.py:113-115) get the MOG2 model on the device as well (`ckb_mog2_apply` in `_learn_bg`,
+bit-identical masks; `get_foreground()` returns the host copy, `is_agitated` reads per-zone counts reduced on the
+device). There is no CPU fallback: without the CUDA library or a GPU the first frame raises.
 """
 import numpy as np
 
@@ -20,6 +22,9 @@ from . import hostapi
 from .hostapi import gsize, E, B, W, CODE_TO_COLOR
 
 MIN_CONFIDENCE = 0.6          # sf_neural.py:18
+TARGET_THRESH = 15            # sf_neural.py:19-21
+TARGET_INCR = 5
+NB_LOOKBACK = 3
 _COLOR_INDEX = {E: 0, B: 1, W: 2}   # nn_manager.py:29-30
 
 
@@ -96,6 +101,45 @@ class NNCacheB200:
         return out
 
 
+class HeatPointB200:
+    """A recent prediction awaiting confirmation (HeatPoint, sf_neural.py:198-244): it is re-checked NB_LOOKBACK times,
+    must pass two thirds of the checks, and lingers a few frames after its energy is spent ("cooling") before the
+    location becomes a target candidate again."""
+
+    def __init__(self, color, confidence, stamp, energy=NB_LOOKBACK):
+        self.target = self.energy = energy
+        self.color, self.confidence, self.stamp = color, confidence, stamp
+        self.nb_checks = self.nb_passed = 0
+
+    @property
+    def live(self):
+        return self.energy > 0
+
+    def check(self, color, confidence):
+        self.nb_checks += 1
+        self.energy -= 1
+        agreed = color == self.color
+        self.nb_passed += int(agreed)
+        # running mean in which the initial confidence counts as the first sample
+        self.confidence = (self.confidence * self.nb_checks + (confidence if agreed else 0)) / (self.nb_checks + 1)
+
+    def is_valid(self):
+        reachable = 2 * self.target / 3 <= self.nb_passed + self.energy
+        if not reachable:
+            self.energy = 0
+            self.confidence = 0.0
+        return reachable
+
+    def is_cold(self):
+        return self.energy < -5
+
+    def cool(self):
+        """What drawing the heat map does to a spent point in the reference (HeatPoint.__repr__ decrements the energy
+        of points with energy <= 0 every time the map is rendered, i.e. once per steady-state frame)."""
+        if self.energy <= 0:
+            self.energy -= 1
+
+
 # ----------------------------------------------------------------------------------------------------- device plumbing
 class _DeviceFrames:
     """Mixin: engine, device frame / canonical buffers, and the `_doframe` that warps on the GPU."""
@@ -130,6 +174,51 @@ class _DeviceFrames:
             return self._d_goban
         t = self._torch.from_numpy(np.ascontiguousarray(img))
         return t.to(self._engine_obj.device)[None]
+
+    # ---- background model on the device (StonesFinder.__init__ learn_bg / _learn_bg / get_foreground)
+    _bg_on = False
+
+    def _enable_bg(self):
+        """Call from __init__ after the base constructor ran with learn_bg=False (no cv2 model is created)."""
+        self._bg_on = True
+        self._bg_state = None
+        self._bg_frames = 0
+        self._d_fg = None
+        self._fg_host = None
+        self._zone_fg = None
+        if not hasattr(self, "bg_init_frames"):
+            video = getattr(self.vmanager, "current_video", None)
+            still = isinstance(video, str) and video.lower().endswith((".png", ".jpg", ".jpeg"))
+            self.bg_init_frames = 0 if still else 50          # stonesfinder.py:115
+
+    def _learn_bg(self):
+        if not self._bg_on:
+            return
+        if not getattr(self, "_goban_on_device", False):
+            raise RuntimeError("the background model runs on the device image produced by _doframe")
+        eng = self._engine()
+        if self._bg_state is None:
+            self._bg_state = eng.mog2_new_state()
+            self._d_fg = self._torch.empty((1, 20 * gsize, 20 * gsize), dtype=self._torch.uint8, device=eng.device)
+        learning = 0.01 if self.total_f_processed < self.bg_init_frames else 0.005      # stonesfinder.py:174
+        eng.mog2_apply(self._d_goban, self._bg_state, self._bg_frames, [learning], out=self._d_fg)
+        self._bg_frames += 1
+        self._zone_fg = eng.zone_fg_counts(self._d_fg)[0].cpu().numpy()
+        self._fg_host = None
+
+    def get_foreground(self):
+        """The foreground mask of the last frame, (S, S) uint8 0 / 255 (stonesfinder.py:502-515)."""
+        if not self._bg_on or self._d_fg is None:
+            raise ValueError("This StonesFinder doesn't seem to be segmenting background. See self.__init__()")
+        if self._fg_host is None:
+            self._fg_host = self._d_fg[0].cpu().numpy()
+        return self._fg_host
+
+    def is_agitated(self, r, c, fg=None, ratio=0.7):
+        """SfNeural.is_agitated (sf_neural.py:178-180): more than `ratio` of the zone rectangle is foreground. The
+        per-zone foreground counts come from the device (ckb_zone_fg_counts); `fg` is accepted for compatibility."""
+        a0, b0, a1, b1 = self.getrect(r, c)
+        return (a1 - a0) * (b1 - b0) * ratio < int(self._zone_fg[r, c])
 
     def _doframe(self, frame):
         self.intersections = None
@@ -212,22 +301,24 @@ def build_classes(Base):
 
     class SfNeuralB200(_DeviceFrames, Base):
         """CNN stones finder (see SfNeural): every frame the 100 overlapping 2x2-intersection patches of the canonical
-        image go through the network in one tensor-core pass. Start-up follows the reference (load the net on frame 0,
-        wait `bg_init_frames`, then `predict_all`); afterwards every region is re-evaluated each frame and submitted
-        with the reference's `predict_moves` rule — the foreground-driven choice of regions (mark_targets /
-        select_targets / lookback, sf_neural.py:72-176) is SURVEY.md section 8(f2), outside the path built here."""
+        image go through the network in one tensor-core pass and the MOG2 background model is updated on the device.
+        The control flow is the reference's (sf_neural.py:36-176): load the net on frame 0, wait `bg_init_frames`,
+        one `predict_all`, then per frame `mark_targets` (zones whose foreground is agitated accumulate heat),
+        `select_targets` (hot regions that have calmed down), `process_targets` (submit what the network sees there)
+        and `lookback` (re-check recent predictions, cancel the inconsistent ones). The reference evaluates the network
+        lazily per region; here all 100 softmax vectors of the frame are already in the cache."""
 
         cnn_params = None   # class-level default: flat float32 blob (camkifu_b200.weights); set before the first frame
 
         def __init__(self, vmanager):
-            super().__init__(vmanager, learn_bg=False)
-            if not hasattr(self, "bg_init_frames"):
-                video = getattr(vmanager, "current_video", None)
-                still = isinstance(video, str) and video.lower().endswith((".png", ".jpg", ".jpeg"))
-                self.bg_init_frames = 0 if still else 50
+            super().__init__(vmanager, learn_bg=False)       # no cv2 model: the background model lives on the device
+            self._enable_bg()
             self.cache = None
             self.has_sampled = False
             self.indices = class_indices()
+            self.targets = np.zeros((gsize, gsize), dtype=np.uint8)     # per-location agitation (wraps like the reference's)
+            self.heatmap = np.ndarray((gsize, gsize), dtype=object)     # recent predictions awaiting confirmation
+            self.heatmap[:] = None
             self._weights_loaded = False
 
         def _learn(self):
@@ -259,13 +350,45 @@ def build_classes(Base):
                 self.has_sampled = True
             else:
                 self._predict(goban_img)
-                self.process_targets([(i, j) for i in range(10) for j in range(10)])
+                self.mark_targets()
+                self.process_targets()
+                self.lookback()
 
         def predict_all(self):
             """SfNeural.predict_all (sf_neural.py:57-70): every non-empty intersection seen with confidence > 0.6."""
             stones, conf, keep = self._last["stones"], self._last["conf"], self._last["keep"]
-            moves = [(CODE_TO_COLOR[stones[r, c]], r, c) for r in range(gsize) for c in range(gsize) if keep[r, c]]
+            moves = []
+            for r in range(gsize):
+                for c in range(gsize):
+                    if keep[r, c]:
+                        color = CODE_TO_COLOR[stones[r, c]]
+                        moves.append((color, r, c))
+                        self.heatmap[r, c] = HeatPointB200(color, conf[r, c], self.total_f_processed)
             self.bulk_update(moves)
+
+        def mark_targets(self, canvas=None):
+            """SfNeural.mark_targets (sf_neural.py:72-84): locations without a pending prediction heat up while their
+            zone is agitated, and every warm location cools by one per frame."""
+            for r in range(gsize):
+                for c in range(gsize):
+                    if self.heatmap[r, c] is None and self.is_agitated(r, c):
+                        self.targets[r, c] += TARGET_INCR
+            self.targets[self.targets > 0] -= 1
+
+        def select_targets(self, canvas=None):
+            """SfNeural.select_targets (sf_neural.py:129-154): regions holding a location hotter than TARGET_THRESH, once
+            none of their zones is agitated any more (ratio 0.5); selecting a region resets its heat."""
+            chosen = []
+            for i in range(10):
+                for j in range(10):
+                    rs, re, cs, ce = subregion(i, j)
+                    if not (self.targets[rs:re, cs:ce] > TARGET_THRESH).any():
+                        continue
+                    if any(self.is_agitated(a, b, ratio=0.5) for a in range(rs, re) for b in range(cs, ce)):
+                        continue
+                    chosen.append((i, j))
+                    self.targets[rs:re, cs:ce] = 0
+            return chosen
 
         def predict_moves(self, targets):
             """SfNeural.predict_moves (sf_neural.py:101-127)."""
@@ -297,19 +420,56 @@ def build_classes(Base):
                 count[W] += 1
             return abs(math.log(count[B] / count[W], 3))
 
-        def process_targets(self, targets):
-            """SfNeural.process_targets (sf_neural.py:86-99) without the heat map: lopsided batches are dropped."""
+        def process_targets(self, targets=None):
+            """SfNeural.process_targets (sf_neural.py:86-99): what the network sees in the selected regions is submitted
+            (a single stone through `suggest`, several through `bulk_update`) unless the batch is lopsided in colour, and
+            every submitted stone becomes a heat point."""
+            if targets is None:
+                targets = self.select_targets()
             moves = self.predict_moves(targets)
             if not len(moves) or not self.get_color_ratio(moves) < 1:
                 return
+            for color, r, c, confidence in moves:
+                self.heatmap[r, c] = HeatPointB200(color, confidence, self.total_f_processed)
             if len(moves) == 1:
                 try:
                     self.suggest(*moves.pop()[0:3], doprint=False)
                 except Exception as de:  # DeletedError of whichever base is in use
                     if type(de).__name__ != "DeletedError":
                         raise
-            elif len(moves):
+                    print(de)
+            else:
                 self.bulk_update([m[0:3] for m in moves])
+
+        def lookback(self, canvas=None):
+            """SfNeural.lookback (sf_neural.py:156-176): a live heat point whose stone is still on the goban is
+            re-predicted every 11th frame; one that can no longer pass two thirds of its checks is cancelled."""
+            stones = self.get_stones()
+            cancelled = []
+            for r in range(gsize):
+                for c in range(gsize):
+                    hp = self.heatmap[r, c]
+                    if hp is None or not hp.live:
+                        continue
+                    if hp.color != stones[r, c]:
+                        self.heatmap[r, c] = None        # someone else changed the location: leave it alone
+                        continue
+                    if 10 < self.total_f_processed - hp.stamp:
+                        hp.stamp = self.total_f_processed
+                        hp.check(*self.cache.predict_stone(r, c))
+                        if not hp.is_valid():
+                            cancelled.append((E, r, c))
+            if cancelled:
+                self.bulk_update(cancelled)
+            for r in range(gsize):
+                for c in range(gsize):
+                    hp = self.heatmap[r, c]
+                    if hp is not None and hp.is_cold():
+                        self.heatmap[r, c] = None
+            for r in range(gsize):                       # the reference renders the map here, which cools spent points
+                for c in range(gsize):
+                    if self.heatmap[r, c] is not None:
+                        self.heatmap[r, c].cool()
 
         def find_stones(self, img, rs=0, re=gsize, cs=0, ce=gsize, **kwargs):
             """The SfMeta delegate contract for the CNN finder: board state of the intersections in [rs, re) x [cs, ce)

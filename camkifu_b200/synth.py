@@ -132,3 +132,54 @@ def make_clip_parallel(seed: int, n: int, H: int, W: int, gsize: int = 19, worke
     with ThreadPoolExecutor(max_workers=workers or min(32, os.cpu_count() or 1)) as ex:
         list(ex.map(one, range(n)))
     return frames, mtx, truth, corners
+
+
+def make_game_clip(seed: int, n: int, H: int, W: int, events=(), gsize: int = 19, p=(0.7, 0.15, 0.15), reach: int = 4):
+    """A fixed-camera 'game' clip: one starting position, and for every event (frame, colour code, r, c) a hand-coloured
+    blob that travels from the lower board edge to intersection (r, c) during `reach` frames, leaves a stone there and
+    withdraws during the next `reach` frames. This is the kind of input the background model (MOG2) and SfNeural's
+    foreground-driven targeting react to. Returns (frames [n,H,W,3], mtx, truth [n,g,g], corners)."""
+    rng = np.random.default_rng(seed)
+    corners = random_corners(rng, H, W)
+    S = 20 * gsize
+    mtx = board_homography(corners, S)
+    inv = np.linalg.inv(mtx)
+    bg = make_background(rng, H, W)
+    stones = random_stones(rng, gsize, p)
+    for (_, _, r, c) in events:
+        stones[r, c] = E
+    frames = np.empty((n, H, W, 3), dtype=np.uint8)
+    truth = np.empty((n, gsize, gsize), dtype=np.uint8)
+
+    def to_frame(x, y):       # canonical (x = column, y = row) -> frame pixel
+        v = inv @ np.array([x, y, 1.0])
+        return v[0] / v[2], v[1] / v[2]
+
+    board_rng_state = rng.bit_generator.state
+    for i in range(n):
+        hand = None
+        for (f0, color, r, c) in events:
+            if i >= f0 + reach:
+                stones[r, c] = color
+            if f0 <= i < f0 + 2 * reach:
+                t = (i - f0 + 1) / reach if i < f0 + reach else (f0 + 2 * reach - i - 1) / reach
+                tx, ty = 10 + 20 * c, 10 + 20 * r
+                sx, sy = tx, S + 60.0           # starts below the board
+                hand = (sx + (tx - sx) * t, sy + (ty - sy) * t)
+        # the board texture is part of the scene, not of the frame: render it from the same generator state each time
+        rng.bit_generator.state = board_rng_state
+        frame = render_frame(rng, H, W, stones, corners, noise=0, background=bg).astype(np.float32)
+        if hand is not None:
+            cx, cy = to_frame(*hand)
+            ex, ey = to_frame(hand[0], hand[1] + 140.0)
+            blob = np.zeros((H, W), np.uint8)
+            rad = max(3, int(0.035 * min(H, W)))
+            cv2.line(blob, (int(cx), int(cy)), (int(ex), int(ey)), 255, 2 * rad, cv2.LINE_AA)
+            cv2.circle(blob, (int(cx), int(cy)), rad, 255, -1, cv2.LINE_AA)
+            a = (blob.astype(np.float32) / 255.0)[:, :, None]
+            frame = frame * (1 - a) + a * np.array([120, 150, 205], np.float32)
+        noise_rng = np.random.default_rng([seed, i])
+        frame += noise_rng.integers(-6, 7, frame.shape).astype(np.float32)
+        frames[i] = np.clip(frame, 0, 255).astype(np.uint8)
+        truth[i] = stones
+    return frames, mtx, truth, corners

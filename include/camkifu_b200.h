@@ -80,6 +80,22 @@ int ckb_warp(ckb_ctx *ctx, const uint8_t *d_frames, int n, int H, int W, size_t 
 int ckb_accumulate(ckb_ctx *ctx, const uint8_t *d_goban, int n, float *d_accu, float alpha, int first,
                    float *d_snapshots, int snap_every, int snap_phase, void *stream);
 
+/* ---- background model ----------------------------------------------------------------------------
+ * Replaces: self.bg_model = cv2.createBackgroundSubtractorMOG2(detectShadows=False)        stonesfinder.py:113-115
+ *           self._fg = self.bg_model.apply(self.goban_img, learningRate=learning)          stonesfinder.py:171-176
+ * d_state: ckb_mog2_state_bytes(ctx) bytes of DEVICE memory owned by the caller, one per finder (the per-pixel Gaussian
+ * mixture: 5 modes x (weight, variance, BGR mean) + mode count); ckb_mog2_reset = a freshly created subtractor.
+ * ckb_mog2_apply feeds n canonical images IN ORDER; frames_before = how many frames the model has already seen (OpenCV's
+ * nframes: the very first frame always learns at rate 1/2), h_learning_rates = the n `learningRate` arguments (HOST;
+ * negative = OpenCV's automatic 1/min(2 nframes, 500)). d_fgmask: n x S x S uint8, 0 or 255, bit-identical to cv2's.
+ * ckb_zone_fg_counts: per zone rectangle (getrect) the number of foreground pixels = np.sum(fg[a0:a1, b0:b1]) / 255, the
+ * quantity SfNeural.is_agitated thresholds (sf_neural.py:178-180); d_counts n x gsize^2 int32. */
+size_t ckb_mog2_state_bytes(const ckb_ctx *ctx);
+int ckb_mog2_reset(ckb_ctx *ctx, void *d_state, void *stream);
+int ckb_mog2_apply(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_state, long long frames_before,
+                   const double *h_learning_rates, uint8_t *d_fgmask, void *stream);
+int ckb_zone_fg_counts(ckb_ctx *ctx, const uint8_t *d_fgmask, int n, int32_t *d_counts, void *stream);
+
 /* ---- K3 + K2 ------------------------------------------------------------------------------------------------------
  * Replaces: SfClustering.find_stones(img, rs, re, cs, ce)                          sf_clustering.py:48-178
  *   = cv2.kmeans(pixels, 3, None, (TERM_CRITERIA_EPS, 15, 3), 3, KMEANS_PP_CENTERS)   :103-104

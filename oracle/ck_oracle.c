@@ -661,3 +661,99 @@ CKO_API void cko_nn_decode(const float *y, uint8_t *stones_out, float *conf_out,
         }
     for (int k = 0; k < 361; k++) keep[k] = stones_out[k] != 0 && conf_out[k] > 0.6f;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * cv2.createBackgroundSubtractorMOG2(detectShadows=False).apply(img 8UC3, learningRate=lr)     [stonesfinder.py:113-115,
+ * 171-176: StonesFinder.__init__ creates the model, _learn_bg applies every canonical frame with lr = 0.01 during the
+ * first bg_init_frames frames and 0.005 afterwards]
+ *
+ * Zivkovic's adaptive Gaussian mixture (OpenCV video/bgfg_gaussmix2.cpp, MOG2Invoker), defaults: history 500,
+ * nmixtures 5, varThreshold (Tb) 16, varThresholdGen (Tg) 9, backgroundRatio (TB) 0.9, varInit 15, varMin 4,
+ * varMax 75, complexity reduction CT 0.05. Per pixel, modes sorted by weight (descending):
+ *   frame counter n (1-based): alpha = lr if n > 1 and lr >= 0, else 1 / min(2 n, history)  (so the first frame
+ *   always uses 0.5); prune = -alpha * CT; all arithmetic float32 without FMA contraction.
+ * State: weight[5], variance[5], mean[5][3], nmodes, laid out here per pixel as 25 floats + 1 byte.
+ * Pinned bit-exactly against cv2 4.13.0 (tests/test_oracle_vs_cv2.py::test_mog2_bit_exact).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define MOG2_NMIX 5
+CKO_API void cko_mog2_apply(const uint8_t *img /*[npix][3]*/, int npix, float *state /*[npix][25]*/, uint8_t *nmodes_io,
+                            int frame_no /*1-based*/, double learning_rate, uint8_t *mask)
+{
+    const int history = 500;
+    const float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f;
+    const double lrd = (learning_rate >= 0 && frame_no > 1) ? learning_rate
+                                                            : 1. / (2 * frame_no < history ? 2 * frame_no : history);
+    const float alphaT = (float)lrd;
+    const float alpha1 = 1.f - alphaT;
+    const float prune = (float)(-lrd * CT);
+    for (int p = 0; p < npix; p++) {
+        float *w = state + (size_t)p * 25, *var = w + 5, *mean = w + 10;
+        const float data[3] = {(float)img[p * 3], (float)img[p * 3 + 1], (float)img[p * 3 + 2]};
+        int background = 0, fits = 0, nmodes = nmodes_io[p];
+        float totalWeight = 0.f;
+        for (int mode = 0; mode < nmodes; mode++) {   /* the bound shrinks as modes are pruned, as in OpenCV */
+            float weight = alpha1 * w[mode] + prune;
+            int swap_count = 0;
+            if (!fits) {
+                const float v = var[mode];
+                float d[3];
+                d[0] = mean[mode * 3] - data[0];
+                d[1] = mean[mode * 3 + 1] - data[1];
+                d[2] = mean[mode * 3 + 2] - data[2];
+                const float dist2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (totalWeight < TB && dist2 < Tb * v) background = 1;
+                if (dist2 < Tg * v) {
+                    fits = 1;
+                    weight += alphaT;
+                    const float k = alphaT / weight;
+                    for (int c = 0; c < 3; c++) mean[mode * 3 + c] -= k * d[c];
+                    float varnew = v + k * (dist2 - v);
+                    varnew = varnew > varMin ? varnew : varMin;
+                    varnew = varnew < varMax ? varnew : varMax;
+                    var[mode] = varnew;
+                    for (int i = mode; i > 0; i--) {
+                        if (weight < w[i - 1]) break;
+                        swap_count++;
+                        float t;
+                        t = w[i]; w[i] = w[i - 1]; w[i - 1] = t;
+                        t = var[i]; var[i] = var[i - 1]; var[i - 1] = t;
+                        for (int c = 0; c < 3; c++) {
+                            t = mean[i * 3 + c]; mean[i * 3 + c] = mean[(i - 1) * 3 + c]; mean[(i - 1) * 3 + c] = t;
+                        }
+                    }
+                }
+            }
+            if (weight < -prune) {
+                weight = 0.f;
+                nmodes--;
+            }
+            w[mode - swap_count] = weight;
+            totalWeight += weight;
+        }
+        float invWeight = 0.f;
+        if (fabsf(totalWeight) > FLT_EPSILON) invWeight = 1.f / totalWeight;
+        for (int mode = 0; mode < nmodes; mode++) w[mode] *= invWeight;
+        if (!fits && alphaT > 0.f) {
+            const int mode = nmodes == MOG2_NMIX ? MOG2_NMIX - 1 : nmodes++;
+            if (nmodes == 1)
+                w[mode] = 1.f;
+            else {
+                w[mode] = alphaT;
+                for (int i = 0; i < nmodes - 1; i++) w[i] *= alpha1;
+            }
+            for (int c = 0; c < 3; c++) mean[mode * 3 + c] = data[c];
+            var[mode] = varInit;
+            for (int i = nmodes - 1; i > 0; i--) {
+                if (alphaT < w[i - 1]) break;
+                float t;
+                t = w[i]; w[i] = w[i - 1]; w[i - 1] = t;
+                t = var[i]; var[i] = var[i - 1]; var[i - 1] = t;
+                for (int c = 0; c < 3; c++) {
+                    t = mean[i * 3 + c]; mean[i * 3 + c] = mean[(i - 1) * 3 + c]; mean[(i - 1) * 3 + c] = t;
+                }
+            }
+        }
+        nmodes_io[p] = (uint8_t)nmodes;
+        mask[p] = background ? 0 : 255;
+    }
+}

@@ -13,6 +13,14 @@ The reference cannot travel to the GPU box, so its outputs on seeded synthetic i
                            reference's own known-answer tests (test/camkifu/stone/test_tmanager.py:18-27)
   neural_decode.npz        NNCache.predict_all_stones + SfNeural.predict_all with a scripted net (nn_cache.py:25-52,
                            sf_neural.py:57-70)
+  background_stream.npz    a StonesFinder with learn_bg=True driven through _doframe for 30 frames of a 160x120 "game"
+                           clip (a hand places two stones): the MOG2 foreground masks of _learn_bg
+                           (stonesfinder.py:113-115,171-176) and the per-zone foreground sums is_agitated reduces them to
+                           (sf_neural.py:178-180)
+  neural_stream.npz        the unmodified SfNeural._find over 48 frames of such a clip (background sampling, initial
+                           assessment, mark_targets / select_targets / process_targets / lookback, sf_neural.py:36-176)
+                           with `net.predict` = the oracle's float32 forward on seeded Glorot weights: every instruction
+                           piped to the controller, per frame, plus the targets / heat-map state
 """
 import os
 import subprocess
@@ -173,14 +181,106 @@ def gen_neural():
     print("neural: kept", len(mv), "moves; conf range", float(st[:, :, 1].min()), float(st[:, :, 1].max()))
 
 
+GAME_EVENTS = [(8, 1, 9, 9), (18, 2, 3, 14)]          # (frame, colour code, r, c)
+NEURAL_EVENTS = [(14, 1, 9, 9), (26, 2, 3, 14), (36, 1, 15, 4)]
+
+
+def gen_background():
+    from oracle import refimport
+    from camkifu_b200 import synth
+    refimport.load()
+    from camkifu.stone.stonesfinder import StonesFinder
+
+    class Plain(StonesFinder):          # the base class with its background model, no detection
+        def _find(self, goban_img):
+            pass
+
+        def _learn(self):
+            pass
+
+    frames, mtx, truth, _ = synth.make_game_clip(5, 30, 120, 160, events=GAME_EVENTS)
+    vm = refimport.FakeVManager(mtx)
+    sf = Plain(vm, learn_bg=True)
+    sf.bg_init_frames = 10              # 50 for videos (stonesfinder.py:115): shortened so that both rates are exercised
+    masks, zones = [], []
+    for i in range(frames.shape[0]):
+        sf._doframe(frames[i].copy())
+        sf.total_f_processed += 1
+        fg = sf.get_foreground() if i >= sf.bg_init_frames else sf._fg
+        masks.append(np.packbits(fg > 0))
+        zones.append([[np.sum(fg[a0:a1, b0:b1]) / 255 for (a0, b0, a1, b1) in [sf.getrect(r, c)]][0]
+                      for r in range(19) for c in range(19)])
+        assert set(np.unique(fg)) <= {0, 255}
+    zones = np.array(zones, dtype=np.int32).reshape(-1, 19, 19)
+    np.savez_compressed(os.path.join(GOLD, "background_stream.npz"), frames=frames, mtx=mtx, masks=np.array(masks),
+                        zone_fg=zones, bg_init_frames=np.int64(sf.bg_init_frames), events=np.array(GAME_EVENTS))
+    print("background: fg pixels per frame", [int(z.sum()) for z in zones])
+
+
+def gen_neural_stream():
+    import cv2
+    from oracle import refimport
+    from oracle import oracle as O
+    from camkifu_b200 import synth, weights
+    refimport.load()
+    from camkifu.stone.nn_manager import NNManager
+    import camkifu.stone.sf_neural as sfn
+
+    params = weights.glorot_params(seed=0)
+    margins = []
+
+    class OracleNet:                    # stands in for the Keras model: float32 forward of the same architecture
+        def predict(self, x):
+            y = O.c_cnn_forward(np.ascontiguousarray(x, dtype=np.uint8), params)
+            top = np.sort(y[0])[-2:]
+            margins.append((float(top[1] - top[0]), float(abs(y[0].max() / y[0].sum() - sfn.MIN_CONFIDENCE))))
+            return y
+
+    NNManager._network = OracleNet()
+    n = 48
+    frames, mtx, truth, _ = synth.make_game_clip(int(os.environ.get("CKB_NS_SEED", "11")), n, 120, 160, events=NEURAL_EVENTS)
+    vm = refimport.FakeVManager(mtx)
+    sf = sfn.SfNeural(vm)
+    sf.bg_init_frames = 10
+    log, targets, heat = [], [], []
+    for i in range(n):
+        n0 = len(vm.controller.piped)
+        sf._doframe(frames[i].copy())
+        sf.total_f_processed += 1
+        for ins, a in vm.controller.piped[n0:]:
+            if ins == "bulk":
+                for m in a[0]:
+                    log.append((i, 0, CODE[m.color], m.y, m.x))
+            elif ins == "append":
+                log.append((i, 1, CODE[a[0].color], a[0].y, a[0].x))
+            elif ins == "delete":
+                log.append((i, 2, 0, a[1], a[0]))
+        targets.append(sf.targets.copy())
+        heat.append(np.array([[0 if h is None else h.energy + 100 for h in row] for row in sf.heatmap], np.int32))
+    np.savez_compressed(os.path.join(GOLD, "neural_stream.npz"), frames=frames, mtx=mtx, truth=truth,
+                        log=np.array(log, dtype=np.int32).reshape(-1, 5), targets=np.array(targets), heat=np.array(heat),
+                        board=codes(vm.controller.stones), bg_init_frames=np.int64(10), events=np.array(NEURAL_EVENTS),
+                        min_label_margin=np.float64(min(m[0] for m in margins)),
+                        min_conf_margin=np.float64(min(m[1] for m in margins)))
+    print("neural stream:", len(log), "piped stone updates over", n, "frames;", len(margins), "net calls; min label margin",
+          min(m[0] for m in margins), "min |conf - 0.6|", min(m[1] for m in margins))
+    NNManager._network = None
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "geometry":
         gen_geometry()
+    elif what == "background":
+        gen_background()
+    elif what == "neural_stream":
+        gen_neural_stream()
     elif what == "all":
         for g in (9, 13, 19):
             subprocess.run([sys.executable, "-m", "oracle.gen_golden", "geometry"], check=True, cwd=ROOT,
                            env=dict(os.environ, CKB_GSIZE=str(g)))
         gen_clustering()
         gen_neural()
+        gen_background()
+        gen_neural_stream()

@@ -54,6 +54,26 @@ def c_accumulate(src, acc, alpha=0.2, first=False):
     return acc
 
 
+class CMog2:
+    """cv2.createBackgroundSubtractorMOG2(detectShadows=False) restated (ck_oracle.c: cko_mog2_apply)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        n = self.shape[0] * self.shape[1]
+        self.state = np.zeros((n, 25), np.float32)
+        self.nmodes = np.zeros(n, np.uint8)
+        self.nframes = 0
+
+    def apply(self, img, learningRate=-1.0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        assert img.shape == self.shape + (3,)
+        self.nframes += 1
+        mask = np.empty(self.shape, np.uint8)
+        lib().cko_mog2_apply(_p(img), C.c_int(self.nmodes.size), _p(self.state), _p(self.nmodes), C.c_int(self.nframes),
+                             C.c_double(learningRate), _p(mask))
+        return mask
+
+
 def rng_seed_state(seed: int) -> int:
     return int(lib().cko_rng_seed_state(seed))
 

@@ -141,3 +141,38 @@ def test_detect_stream_matches_synchronous_calls():
         for h, m in batches[1:4]:
             pipe.submit(h, m)
         pipe.collect(t0)           # its slot has been reused: at most DEPTH batches may be outstanding
+
+
+def test_sfneural_stream_matches_reference(golden):
+    """neural_stream.npz: the unmodified SfNeural._find over a 48-frame 'game' clip (background sampling, initial
+    assessment, foreground-driven targeting, look-back), with net.predict = the oracle's float32 forward. The plugin —
+    MOG2 and the CNN on the device — must send the controller the same stone updates on the same frames, and carry the
+    same targets / heat-map state. (Within one frame the reference iterates a Python set: order is not defined.)"""
+    g = golden("neural_stream.npz")
+    frames, mtx, log = g["frames"], g["mtx"], g["log"]
+    vm = HeadlessVManager(mtx)
+    plugins.SfNeuralB200.cnn_params = weights.glorot_params(seed=0)
+    try:
+        sf = plugins.SfNeuralB200(vm)
+        sf.bg_init_frames = int(g["bg_init_frames"])
+        for i in range(frames.shape[0]):
+            n0 = len(vm.controller.piped)
+            sf._doframe(frames[i].copy())
+            sf.total_f_processed += 1
+            got = set()
+            for ins, a in vm.controller.piped[n0:]:
+                if ins == "bulk":
+                    got |= {(0, CODE[m.color], m.y, m.x) for m in a[0]}
+                elif ins == "append":
+                    got.add((1, CODE[a[0].color], a[0].y, a[0].x))
+                elif ins == "delete":
+                    got.add((2, 0, a[1], a[0]))
+            want = {tuple(int(v) for v in row[1:]) for row in log[log[:, 0] == i]}
+            assert got == want, "frame %d: %s vs %s" % (i, sorted(got ^ want)[:6], len(want))
+            assert np.array_equal(sf.targets, g["targets"][i]), "targets after frame %d" % i
+            heat = np.array([[0 if h is None else h.energy + 100 for h in row] for row in sf.heatmap], np.int32)
+            assert np.array_equal(heat, g["heat"][i]), "heat map after frame %d" % i
+    finally:
+        plugins.SfNeuralB200.cnn_params = None
+    assert np.array_equal(codes(vm.controller.stones), g["board"])
+    assert len(log) > 100 and g["targets"].max() > plugins.TARGET_THRESH     # the clip exercised the steady state

@@ -106,3 +106,19 @@ def test_neural_decode(golden, oracle):
     assert np.array_equal(conf, g["conf"])
     moves = np.array([(stones[r, c], r, c) for r in range(19) for c in range(19) if keep[r, c]], np.int32)
     assert np.array_equal(moves.reshape(-1, 3), g["moves"])
+
+
+def test_background_stream(golden, oracle):
+    """background_stream.npz: the reference's StonesFinder (learn_bg=True) driven through _doframe. The oracle's warp +
+    MOG2 restatement reproduces every foreground mask and the per-zone sums SfNeural.is_agitated thresholds."""
+    g = golden("background_stream.npz")
+    frames, mtx, init = g["frames"], g["mtx"], int(g["bg_init_frames"])
+    model = oracle.CMog2((380, 380))
+    rects = oracle.c_zone_rects(19)
+    for i in range(frames.shape[0]):
+        goban = oracle.c_warp(frames[i], mtx, 380)
+        fg = model.apply(goban, 0.01 if i < init else 0.005)
+        assert np.array_equal(np.packbits(fg > 0), g["masks"][i]), "frame %d" % i
+        zones = np.array([[int((fg[a0:a1, b0:b1] > 0).sum()) for (a0, b0, a1, b1) in rects[r]] for r in range(19)])
+        assert np.array_equal(zones, g["zone_fg"][i])
+    assert g["zone_fg"][12].max() > 200     # the hand covers whole zones mid-clip

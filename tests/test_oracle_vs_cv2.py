@@ -82,3 +82,30 @@ def test_cnn_oracle_vs_torch_and_f64(oracle):
     assert np.abs(z32 - z64).max() <= 1e-4 * scale
     assert np.abs(y32 - y64).max() <= 1e-3 and np.abs(yt - y64).max() <= 1e-3
     assert np.array_equal(y32.argmax(1), y64.argmax(1)) and np.array_equal(yt.argmax(1), y64.argmax(1))
+
+
+@pytest.mark.parametrize("rates", ["reference", "auto", "fast", "mixed"])
+def test_mog2_bit_exact(oracle, rates):
+    """cko_mog2_apply against cv2.createBackgroundSubtractorMOG2(detectShadows=False).apply — the call of
+    StonesFinder._learn_bg (stonesfinder.py:171-176) — on a noisy scene with moving and appearing objects: every mask
+    of the stream is bit-identical (mode creation, matching, re-sorting, pruning, the first-frame rate of 1/2)."""
+    import cv2
+    rng = np.random.default_rng(3)
+    S, n = 96, 90
+    bg = rng.integers(0, 256, (S, S, 3)).astype(np.int16)
+    ref = cv2.createBackgroundSubtractorMOG2(detectShadows=False)
+    mine = oracle.CMog2((S, S))
+    fg_seen = 0
+    for i in range(n):
+        f = bg + rng.integers(-12, 13, (S, S, 3))
+        if i > 20:
+            x = (i * 3) % (S - 20)
+            f[30:50, x:x + 20] = rng.integers(0, 256, 3)
+        if 50 < i < 75:
+            f[60:80, 10:40] += 60
+        f = np.clip(f, 0, 255).astype(np.uint8)
+        lr = {"reference": 0.01 if i < 50 else 0.005, "auto": -1.0, "fast": 0.2, "mixed": (-1.0, 0.01, 0.3, 0.0)[i % 4]}[rates]
+        a, b = ref.apply(f, learningRate=lr), mine.apply(f, lr)
+        assert np.array_equal(a, b), "frame %d: %d pixels differ" % (i, int((a != b).sum()))
+        fg_seen += int((a > 0).sum()) if i > 0 else 0
+    assert fg_seen > 10000      # the scene did produce foreground

@@ -97,3 +97,30 @@ def test_registration_with_reference_vmanager():
     # instantiation the way check_sf does it (vmanager.py:367): sf_class(vmanager), no GPU needed yet
     sf = Sc(refimport.FakeVManager(None))
     assert sf.canonical_shape == (380, 380) and sf.getrect(18, 18) == (360, 360, 379, 379)
+
+
+def test_heat_point_mirrors_reference():
+    """HeatPointB200 against the reference's HeatPoint (sf_neural.py:198-244) under random check / render sequences,
+    including the energy decrement that rendering the heat map performs on spent points."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference tree not present")
+    refimport.load()
+    import camkifu.stone.sf_neural as sfn
+    from camkifu_b200 import plugins
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        color = ('B', 'W')[trial % 2]
+        a = sfn.HeatPoint(color, 0.9, 5)
+        b = plugins.HeatPointB200(color, 0.9, 5)
+        for step in range(14):
+            if (a == sfn.HeatPoint) and rng.random() < 0.6:
+                c, conf = ('B', 'W', 'E')[rng.integers(3)], float(rng.random())
+                a.check(c, conf)
+                b.check(c, conf)
+                assert a.is_valid() == b.is_valid()
+            str(a)                      # what _drawvalues does every steady-state frame
+            b.cool()
+            assert (a.energy, a.nb_checks, a.nb_passed) == (b.energy, b.nb_checks, b.nb_passed)
+            assert a.confidence == b.confidence
+            assert (a == sfn.HeatPoint) == b.live and (a == sfn.COLD) == b.is_cold()
