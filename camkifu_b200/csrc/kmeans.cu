@@ -13,11 +13,13 @@
 // All of it is reproduced bit for bit. Distances and all the independent per-pixel work run in parallel; float64
 // sums are taken in a fixed (deterministic) tree order — they are exact whenever OpenCV's are, which holds for pixel
 // data (float32 terms spanning < 29 binades) — and the one inherently serial piece, the float32 centre sums, is
-// executed serially: the CTA computes the labels of a 512-pixel chunk in parallel, writes the per-(cluster, channel)
-// masked values to shared memory, and nine lanes of warp 0 then walk the chunk in pixel order with one dependent
-// FADD per pixel each (adding +0 for non-members is exact). The dependent-add latency (4 cycles) bounds an iteration
-// at ~0.3 ms for a whole board, so throughput comes from running many (frame, attempt) CTAs side by side: grid =
-// 3 attempts x n frames, 256 threads, 8 CTAs per SM.
+// executed serially where it has to be: the CTA computes the labels of a 512-pixel chunk in parallel, writes the
+// per-(cluster, channel) masked values to shared memory, and nine lanes of warp 0 then walk the chunk in pixel order
+// with one dependent FADD per pixel each (adding +0 for non-members is exact). The dependent-add latency (4 cycles)
+// bounds such an iteration at ~0.3 ms for a whole board. For uint8 images (the canonical image itself, as opposed
+// to SfClustering's float32 running average) the sums are integers that float32 represents exactly below 2^24, so
+// the serial walk is only needed from the chunk where a running sum first passes 2^24 — see the Lloyd loop.
+// Throughput comes from running many (frame, attempt) CTAs side by side: grid = 3 attempts x n frames, 256 threads.
 //
 // Kernels:  ckb_pack_region_*   region pixels -> linear, vector-loadable scratch (uchar4 / float4 per pixel)
 //           ckb_kmeans_attempt  one CTA per (frame, attempt)
@@ -27,13 +29,14 @@
 
 #include "ckb_common.cuh"
 
-#define KM_THREADS 256
-#define KM_WARPS (KM_THREADS / 32)
+#define KM_THREADS_F32 256             // float32 input: the serial centre sums dominate, many small CTAs per SM
+#define KM_MAX_WARPS 32
 #define KM_SEG 256                     // pixels per warp segment in the k-means++ passes
 #define KM_MAX_N (380 * 380)
 #define KM_MAX_SEG ((KM_MAX_N + KM_SEG - 1) / KM_SEG)   // 565
 #define KM_CH 512                      // pixels per Lloyd chunk
 #define KM_PLANE (KM_CH + 4)           // +4 words: the nine lanes' 128-bit reads fall in distinct banks
+#define KM_MAX_CHUNK ((KM_MAX_N + KM_CH - 1) / KM_CH)   // 283
 #define KM_MAX_ITER 100                // criteria type has EPS only => maxCount = 100 (the "15" is ignored)
 #define KM_EPS2 9.0                    // (eps = 3)^2
 
@@ -143,8 +146,10 @@ struct __align__(16) KmShared {
         double segsum[4][KM_MAX_SEG + 3];  // [0] current dist, [1..3] the three trial candidates   (k-means++)
         float planes[9][KM_PLANE];         // masked values per (cluster, channel) of one chunk     (Lloyd)
     } u;
-    double red_d[KM_WARPS * 3];
-    int red_i[KM_WARPS * 4];
+    int csum[9][KM_MAX_CHUNK];             // uint8 input: exact integer member sums per chunk         (Lloyd)
+    int ch0;                               // first chunk whose float32 running sums must be taken serially
+    double red_d[KM_MAX_WARPS * 3];
+    int red_i[KM_MAX_WARPS * 4];
     float cen[9];
     float oldc[9];
     float sums[9];
@@ -208,13 +213,13 @@ __device__ int pp_sample(const void *px, int N, int nseg, const double *segsum, 
 
 // one k-means++ pass: for ncand candidate centres (pixel indices in sh.cand) compute min(d(x, cand), base) summed per
 // segment into segsum[1 + c][seg]; ncen == 0 means "no base" (the very first centre).
-template <bool F32>
+template <bool F32, int NW>
 __device__ void pp_pass(const void *px, int N, int nseg, KmShared &sh, int ncen, int ncand, int warp, int lane)
 {
     float3 cd[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) cd[c] = load_px<F32>(px, sh.cand[c < ncand ? c : 0]);
-    for (int seg = warp; seg < nseg; seg += KM_WARPS) {
+    for (int seg = warp; seg < nseg; seg += NW) {
         double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < KM_SEG / 32; j++) {
@@ -250,12 +255,13 @@ __device__ void pp_pass(const void *px, int N, int nseg, KmShared &sh, int ncen,
     __syncthreads();
 }
 
-template <bool F32>
-__global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__restrict__ scratch,
+template <bool F32, int NT>
+__global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict__ scratch,
                                                                  size_t scratch_stride, int N,
                                                                  const uint64_t *__restrict__ rng_states,
                                                                  KmAttempt *__restrict__ results)
 {
+    constexpr int NW = NT / 32;
     __shared__ KmShared sh;
     const int attempt = blockIdx.x, frame = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -273,12 +279,12 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
     // ---- k-means++ seeding
     if (tid == 0) { sh.cand[0] = c0; sh.cand[1] = c0; sh.cand[2] = c0; }
     __syncthreads();
-    pp_pass<F32>(px, N, nseg, sh, 0, 1, warp, lane);
+    pp_pass<F32, NW>(px, N, nseg, sh, 0, 1, warp, lane);
     if (tid < 3) {
         const float3 x = load_px<F32>(px, c0);
         sh.cen[tid] = tid == 0 ? x.x : (tid == 1 ? x.y : x.z);
     }
-    for (int s = tid; s < nseg; s += KM_THREADS) sh.u.segsum[0][s] = sh.u.segsum[1][s];
+    for (int s = tid; s < nseg; s += NT) sh.u.segsum[0][s] = sh.u.segsum[1][s];
     if (tid == 0) sh.dtmp[0] = sh.dtmp[1];  // sum0
     __syncthreads();
     for (int k = 1; k < 3; k++) {
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
             if (lane == 0) sh.cand[warp] = ci;
         }
         __syncthreads();
-        pp_pass<F32>(px, N, nseg, sh, k, 3, warp, lane);
+        pp_pass<F32, NW>(px, N, nseg, sh, k, 3, warp, lane);
         // best trial: strict '<' in trial order
         int best = 0;
         double bs = sh.dtmp[1];
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
             const float3 x = load_px<F32>(px, sh.cand[best]);
             sh.cen[3 * k + tid] = tid == 0 ? x.x : (tid == 1 ? x.y : x.z);
         }
-        for (int s = tid; s < nseg; s += KM_THREADS) sh.u.segsum[0][s] = sh.u.segsum[1 + best][s];
+        for (int s = tid; s < nseg; s += NT) sh.u.segsum[0][s] = sh.u.segsum[1 + best][s];
         if (tid == 0) sh.dtmp[0] = bs;
         __syncthreads();
     }
@@ -315,26 +321,88 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
 #pragma unroll
         for (int k = 0; k < 9; k++) oc[k] = sh.oldc[k];
 
-        // centre sums: parallel labelling per chunk, then the sequential float32 adds on nine lanes of warp 0
+        // centre sums. OpenCV adds the members of a cluster in pixel order in float32. For uint8-valued pixels every
+        // partial sum below 2^24 is an integer that float32 holds exactly, so up to that point the order does not
+        // matter: pass 1 labels all pixels and takes exact integer sums per 512-pixel chunk fully in parallel (one
+        // warp per chunk, no block barrier), a nine-lane prefix over the chunk sums finds the first chunk in which
+        // any (cluster, channel) running sum could pass 2^24, and only from that chunk on (`ch0`; typically the last
+        // few chunks of the largest cluster's brightest channel, often none) are the adds executed serially as for
+        // float32 input: the CTA labels a chunk in parallel, writes the per-(cluster, channel) masked values to shared
+        // memory, and nine lanes of warp 0 walk it in pixel order with one dependent FADD per pixel each.
         float acc = 0.f;
         int c0n = 0, c1n = 0, c2n = 0;
-        float3 xn[2];
-        bool vn[2];
+        int ch0 = 0;
+        if (!F32) {
+            for (int ch = warp; ch < nchunk; ch += NW) {
+                int s9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+                for (int j = 0; j < KM_CH / 32; j++) {
+                    const int i = ch * KM_CH + j * 32 + lane;
+                    if (i < N) {
+                        const float3 x = load_px<F32>(px, i);
+                        const int lab = argmin3(x, oc);
+                        const int vx = (int)x.x, vy = (int)x.y, vz = (int)x.z;
+                        c0n += lab == 0;
+                        c1n += lab == 1;
+                        c2n += lab == 2;
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int i = q * KM_THREADS + tid;
-            vn[q] = i < N;
+                        for (int k = 0; k < 3; k++) {
+                            const int m = lab == k;
+                            s9[3 * k + 0] += m * vx;
+                            s9[3 * k + 1] += m * vy;
+                            s9[3 * k + 2] += m * vz;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 9; c++) {
+                    const int t = __reduce_add_sync(0xffffffffu, s9[c]);
+                    if (lane == 0) sh.csum[c][ch] = t;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int first = nchunk, run = 0;
+                if (lane < 9) {
+                    for (int ch = 0; ch < nchunk; ch++) {
+                        run += sh.csum[lane][ch];
+                        if (run > (1 << 24)) { first = ch; break; }   // a partial sum inside chunk ch may need rounding
+                    }
+                }
+                first = __reduce_min_sync(0xffffffffu, first);
+                run = 0;
+                if (lane < 9) {
+                    for (int ch = 0; ch < first; ch++) run += sh.csum[lane][ch];
+                    sh.sums[lane] = (float)run;                       // exact: run <= 2^24
+                }
+                if (lane == 0) sh.ch0 = first;
+            }
+            __syncthreads();
+            ch0 = sh.ch0;
+            if (warp == 0 && lane < 9) acc = sh.sums[lane];
+        }
+        constexpr int Q = (KM_CH + NT - 1) / NT;     // chunk pixels per thread in the serial phase
+        float3 xn[Q];
+        bool vn[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int p = q * NT + tid;
+            const int i = ch0 * KM_CH + p;
+            vn[q] = p < KM_CH && i < N;
             xn[q] = vn[q] ? load_px<F32>(px, i) : make_float3(0.f, 0.f, 0.f);
         }
-        for (int ch = 0; ch < nchunk; ch++) {
+        for (int ch = ch0; ch < nchunk; ch++) {
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int p = q * KM_THREADS + tid;
+            for (int q = 0; q < Q; q++) {
+                const int p = q * NT + tid;
+                if (p >= KM_CH) continue;
                 const float3 x = xn[q];
                 const int lab = vn[q] ? argmin3(x, oc) : -1;
-                c0n += lab == 0;
-                c1n += lab == 1;
-                c2n += lab == 2;
+                if (F32) {          // uint8 input counted its members in pass 1
+                    c0n += lab == 0;
+                    c1n += lab == 1;
+                    c2n += lab == 2;
+                }
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const bool m = lab == k;
@@ -369,7 +437,7 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
         __syncthreads();
         if (tid < 3) {
             int t = 0;
-            for (int w = 0; w < KM_WARPS; w++) t += sh.red_i[w * 4 + tid];
+            for (int w = 0; w < NW; w++) t += sh.red_i[w * 4 + tid];
             sh.cnt[tid] = t;
         }
         __syncthreads();
@@ -385,7 +453,7 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
             // farthest: `if (max_dist <= dist)` in index order => largest distance, last index among ties
             float bestd = -1.f;
             int besti = -1;
-            for (int i = tid; i < N; i += KM_THREADS) {
+            for (int i = tid; i < N; i += NT) {
                 const float3 x = load_px<F32>(px, i);
                 int lab = argmin3(x, oc);
                 for (int q = 0; q < sh.n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
@@ -404,7 +472,7 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
             if (tid == 0) {
                 double bd = sh.red_d[0];
                 int bi = sh.red_i[0];
-                for (int w = 1; w < KM_WARPS; w++)
+                for (int w = 1; w < NW; w++)
                     if (sh.red_d[w] > bd || (sh.red_d[w] == bd && sh.red_i[w] > bi)) { bd = sh.red_d[w]; bi = sh.red_i[w]; }
                 const float3 x = load_px<F32>(px, bi);
                 sh.cnt[max_k]--;
@@ -451,18 +519,23 @@ __global__ void __launch_bounds__(KM_THREADS) ckb_kmeans_attempt(const void *__r
 #pragma unroll
         for (int k = 0; k < 9; k++) { oc[k] = sh.oldc[k]; nc[k] = sh.cen[k]; }
         double acc = 0.0;
-        for (int i = tid; i < N; i += KM_THREADS) {
+        const int n_fix = sh.n_fix;
+#pragma unroll 4
+        for (int i = tid; i < N; i += NT) {
             const float3 x = load_px<F32>(px, i);
             int lab = argmin3(x, oc);
-            for (int q = 0; q < sh.n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
-            acc += (double)dist3(x.x, x.y, x.z, nc[3 * lab], nc[3 * lab + 1], nc[3 * lab + 2]);
+            for (int q = 0; q < n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
+            const float cx = lab == 0 ? nc[0] : (lab == 1 ? nc[3] : nc[6]);
+            const float cy = lab == 0 ? nc[1] : (lab == 1 ? nc[4] : nc[7]);
+            const float cz = lab == 0 ? nc[2] : (lab == 1 ? nc[5] : nc[8]);
+            acc += (double)dist3(x.x, x.y, x.z, cx, cy, cz);
         }
         acc = warp_sum_d(acc);
         if (lane == 0) sh.red_d[warp] = acc;
         __syncthreads();
         if (tid == 0) {
             double t = 0.0;
-            for (int w = 0; w < KM_WARPS; w++) t += sh.red_d[w];
+            for (int w = 0; w < NW; w++) t += sh.red_d[w];
             KmAttempt &r = results[frame * 3 + attempt];
             r.compactness = t;
             for (int k = 0; k < 9; k++) { r.centers[k] = sh.cen[k]; r.old_centers[k] = sh.oldc[k]; }
@@ -642,7 +715,7 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
     if (is_f32) {
         ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
         CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        ckb_kmeans_attempt<true><<<dim3(3, n), KM_THREADS, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        ckb_kmeans_attempt<true, KM_THREADS_F32><<<dim3(3, n), KM_THREADS_F32, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
         CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
         ckb_zone_classify<true><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
                                                           ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
@@ -651,7 +724,12 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
     } else {
         ckb_pack_region<false><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
         CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        ckb_kmeans_attempt<false><<<dim3(3, n), KM_THREADS, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        // uint8 input: the passes are parallel and bound by L2 load latency / instruction issue: wide CTAs. Measured on
+        // B200 (full board): 64 frames 1.99 / 1.52 / 1.21 ms with 256 / 512 / 1024 threads, 512 frames 5.96 / 4.64 / 5.08 ms
+        if (n <= 128)
+            ckb_kmeans_attempt<false, 1024><<<dim3(3, n), 1024, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        else
+            ckb_kmeans_attempt<false, 512><<<dim3(3, n), 512, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
         CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
         ckb_zone_classify<false><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
                                                            ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
