@@ -471,8 +471,24 @@ int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
     pack_layer<Conv1Cfg>(h, L.off_w[0], L.off_b[0],
                          [&](int t, int k, int n) { return k < 15 ? w1[((t * 5 + k / 3) * 3 + k % 3) * 32 + n] : 0.f; },
                          p + OFF_B1, 32);
-    pack_layer<Conv2Cfg>(h, L.off_w[1], L.off_b[1], [&](int t, int k, int n) { return w2[(t * 32 + k) * 32 + n]; },
-                         p + OFF_B2, 32);
+    // conv2 for cnn_tc_front's pixel-pair formulation: per (dy, 8-channel chunk) the chain of tap blocks dx = 4..0, each
+    // 64 rows = W_hi / W_lo of the 32 output channels interleaved in groups of 8 rows: [H0-7 L0-7 H8-15 L8-15 ...]
+    {
+        uint16_t *w = (uint16_t *)(h + L.off_w[1]);
+        for (int dy = 0; dy < 5; dy++)
+            for (int c = 0; c < 4; c++)
+                for (int dx = 0; dx < 5; dx++)
+                    for (int co = 0; co < 32; co++)
+                        for (int e = 0; e < 8; e++) {
+                            const float f = w2[(((dy * 5 + dx) * 32) + c * 8 + e) * 32 + co];
+                            const uint16_t hi = bf16_rn(f), lo = bf16_rn(f - bf16_f(hi));
+                            const size_t base = ((size_t)(dy * 4 + c) * 5 + (4 - dx)) * 512;   // in bf16 elements (1 KB per tap block)
+                            w[base + (2 * (co / 8)) * 64 + (co % 8) * 8 + e] = hi;
+                            w[base + (2 * (co / 8) + 1) * 64 + (co % 8) * 8 + e] = lo;
+                        }
+        float *b = (float *)(h + L.off_b[1]);
+        for (int n = 0; n < 32; n++) b[n] = p[OFF_B2 + n];
+    }
     pack_layer<Conv3Cfg>(h, L.off_w[2], L.off_b[2],
                          [&](int t, int k, int n) { return n < 90 ? w3[(t * 32 + k) * 90 + n] : 0.f; }, p + OFF_B3, 90);
     pack_layer<Conv4Cfg>(h, L.off_w[3], L.off_b[3],
