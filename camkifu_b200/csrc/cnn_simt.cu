@@ -170,17 +170,106 @@ int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softm
     return CKB_OK;
 }
 
-// Tail of the tensor-core path (cnn_tc.cu): fc2 (160 -> 81, 13 k MAC per patch, float32 FMA) + softmax + decode.
-// d_tmp: n*100*(81 + 81 + 2) floats.
+// Tail of the tensor-core path (cnn_tc.cu): fc2 (Dense(81), nn_manager.py:295; 13 k MAC per patch, float32 FMA in the
+// same sequential order as cnn_dense_simt) + softmax + label / confidence in one kernel. One warp per region: the 160
+// inputs sit in registers (5 per lane) and are broadcast by shuffles, each lane owns outputs lane, lane + 32, lane + 64,
+// the 160 x 81 weights are staged once per block in shared memory.
+#define FC2_THREADS 256
+#define FC2_SMEM ((CNN_F5 * CNN_F6 + CNN_F6) * 4)
+__global__ void __launch_bounds__(FC2_THREADS) cnn_fc2_softmax_label(const float *__restrict__ f5, const float *__restrict__ w,
+                                                                     const float *__restrict__ b, int n_regions,
+                                                                     float *__restrict__ softmax, int *__restrict__ label,
+                                                                     float *__restrict__ conf)
+{
+    extern __shared__ float s_w[];                       // [160][81] weights, then [81] biases
+    for (int i = threadIdx.x; i < CNN_F5 * CNN_F6; i += FC2_THREADS) s_w[i] = __ldg(w + i);
+    for (int i = threadIdx.x; i < CNN_F6; i += FC2_THREADS) s_w[CNN_F5 * CNN_F6 + i] = __ldg(b + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool has2 = lane + 64 < CNN_F6;
+    for (int reg = blockIdx.x * (FC2_THREADS / 32) + wib; reg < n_regions; reg += gridDim.x * (FC2_THREADS / 32)) {
+        const float *x = f5 + (size_t)reg * CNN_F5;
+        float xin[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) xin[k] = __ldg(x + 32 * k + lane);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) {
+                const float xi = __shfl_sync(0xffffffffu, xin[k], l);
+                const float *wr = s_w + (32 * k + l) * CNN_F6;
+                a0 = fmaf(xi, wr[lane], a0);
+                a1 = fmaf(xi, wr[lane + 32], a1);
+                if (has2) a2 = fmaf(xi, wr[lane + 64], a2);
+            }
+        }
+        float v[3];
+        v[0] = a0 + s_w[CNN_F5 * CNN_F6 + lane];
+        v[1] = a1 + s_w[CNN_F5 * CNN_F6 + lane + 32];
+        v[2] = has2 ? a2 + s_w[CNN_F5 * CNN_F6 + lane + 64] : -INFINITY;
+        float m = fmaxf(fmaxf(v[0], v[1]), v[2]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = (lane + 32 * k) < CNN_F6 ? expf(v[k] - m) : 0.f;
+            s += v[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        float *y = softmax + (size_t)reg * CNN_F6;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = __fdiv_rn(v[k], s);
+            if (lane + 32 * k < CNN_F6) y[lane + 32 * k] = v[k];
+        }
+        // label = first maximum (np.argmax); confidence = max(y) / sum(y) with Python's sequential float32 sum
+        // (nn_cache.py:28-30): lane 0 walks the 81 values in order, fetching them from their owners by shuffle
+        int best = 0;
+        float bv = 0.f, tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll 9
+            for (int l = 0; l < 32; l++) {
+                const float t = __shfl_sync(0xffffffffu, v[k], l);
+                const int o = 32 * k + l;
+                if (o < CNN_F6) {
+                    if (o == 0 || t > bv) { bv = t; best = o; }
+                    tot = __fadd_rn(tot, t);
+                }
+            }
+        }
+        if (lane == 0) {
+            label[reg] = best;
+            conf[reg] = __fdiv_rn(bv, tot);
+        }
+    }
+}
+
+// d_tmp: n*100*(81 + 2) floats (softmax when the caller does not want it, labels, confidences)
 int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, float *d_softmax, uint8_t *d_stones,
                           float *d_conf, uint8_t *d_keep, cudaStream_t st)
 {
     const int P = n * 100;
     const float *w = ctx->cnn->d_params;
-    float *logits = (float *)d_tmp;
-    cnn_dense_simt<160, 81, false><<<(unsigned)(((long long)P * CNN_F6 + 255) / 256), 256, 0, st>>>(d_f5, w + OFF_W6, w + OFF_B6, logits, P);
-    CKB_LAUNCH_CHECK(ctx, "cnn_fc2");
-    return ckb_launch_decode(ctx, logits, n, d_softmax, logits + (size_t)P * CNN_F6, d_stones, d_conf, d_keep, st);
+    float *sm = d_softmax ? d_softmax : (float *)d_tmp;
+    int *lab = (int *)((float *)d_tmp + (size_t)P * CNN_F6);
+    float *cf = (float *)(lab + P);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_fc2_softmax_label, cudaFuncAttributeMaxDynamicSharedMemorySize, FC2_SMEM));
+        attr_set = true;
+    }
+    const int per_block = FC2_THREADS / 32;
+    int grid = (P + per_block - 1) / per_block;
+    if (grid > 2 * ctx->num_sms) grid = 2 * ctx->num_sms;
+    cnn_fc2_softmax_label<<<grid, FC2_THREADS, FC2_SMEM, st>>>(d_f5, w + OFF_W6, w + OFF_B6, P, sm, lab, cf);
+    CKB_LAUNCH_CHECK(ctx, "cnn_fc2_softmax_label");
+    cnn_decode_board<<<(n * 361 + 127) / 128, 128, 0, st>>>(lab, cf, n, d_stones, d_conf, d_keep);
+    CKB_LAUNCH_CHECK(ctx, "cnn_decode_board");
+    return CKB_OK;
 }
 
 // workspace of the SIMT path, floats per patch

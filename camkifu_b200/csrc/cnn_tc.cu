@@ -38,31 +38,31 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
 // ------------------------------------------------------------------------------------------------------ layer configs
 struct Conv1Cfg {   // input: 16-channel "row window" expansion of the patch (k = dx*3 + c), taps = dy
     static constexpr int NTAPS = 5, GW = 40, HW_IN = 1600, OH = 36, OW = 36, KC = 2, N = 32, A_PLANES = 1;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
     static constexpr int KCS = 2, NSTAGE = 1, NABUF = 6, NACC = 4;   // tiny tiles: latency bound without depth
     __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
 };
 struct Conv2Cfg {
     static constexpr int NTAPS = 25, GW = 36, HW_IN = 1296, OH = 32, OW = 32, KC = 4, N = 32, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 5) * 36 + t % 5; }
 };
 struct Conv3Cfg {
     static constexpr int NTAPS = 9, GW = 16, HW_IN = 256, OH = 14, OW = 14, KC = 4, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 3, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 16 + t % 3; }
 };
-struct Conv4Cfg {
+struct Conv4Cfg {   // POOL_X: the epilogue already takes the horizontal half of the 2x2 max-pool that follows
     static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false, POOL_X = true;
     static constexpr int KCS = 6, NSTAGE = 4, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
 };
 struct Fc1Cfg {     // "pixels" are patches; tap q = pooled pixel, its A tile is streamed with its weights
     static constexpr int NTAPS = 36, GW = 1, HW_IN = 1, OH = 1, OW = 1, KC = 12, N = 160, A_PLANES = 2;
-    static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true;
+    static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true, POOL_X = false;
     static constexpr int KCS = 4, NSTAGE = 5, NABUF = 0, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int) { return 0; }
 };
@@ -276,8 +276,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
             const int patch = p / L::HW_IN;
             const int rem = p - patch * L::HW_IN;
             const int y = rem / L::GW, x = rem - y * L::GW;
-            const bool valid = patch < args.n_patches && y < L::OH && x < L::OW;
-            const long long opix = (long long)patch * (L::OH * L::OW) + y * L::OW + x;
+            const bool valid = patch < args.n_patches && y < L::OH && x < L::OW && !(L::POOL_X && (x & 1));
+            // POOL_X: rows m, m+1 of a tile are horizontally adjacent pixels (tile starts and grid widths are even);
+            // the even one keeps max(x, x+1) and the output grid is OH x OW/2
+            const long long opix = L::POOL_X ? (long long)patch * (L::OH * L::OW / 2) + y * (L::OW / 2) + (x >> 1)
+                                             : (long long)patch * (L::OH * L::OW) + y * L::OW + x;
             mbar_wait(b_tfull + 8 * acc, (i / D::NACC) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
@@ -299,6 +302,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
                 v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
                 v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f);
                 v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
+                if (L::POOL_X) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], 1));
+                }
                 if (valid) {
                     if (L::OUT_F32) {
                         float4 *o = (float4 *)(args.out_f32 + opix * L::N + 8 * j);
@@ -337,55 +344,33 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float *v
     }
 }
 
-// 2x2 max pooling of hi/lo planes. in: [2][KC][in_plane] on a W x W grid per patch; out pixel index is
-//   patch * (W/2)^2 + oy * (W/2) + ox          (TO_FC = false: next conv's grid)
-//   ((oy * (W/2) + ox) * KC + chunk) * out_plane + patch   (TO_FC = true: fc1's per-tap planes)
-template <int W, int KC, bool TO_FC>
-__global__ void __launch_bounds__(256) cnn_tc_pool(const uint4 *__restrict__ in, long long in_plane, int n_patches,
-                                                   uint4 *__restrict__ out, long long out_plane)
+// Vertical half of the 2x2 max pooling after conv4 (its epilogue already took the horizontal half): hi/lo planes
+// [2][KC][in_plane] on an H x WP grid per patch -> fc1's per-tap planes, tap q = oy * WP + ox:
+//   out[((q * KC + chunk) * out_plane + patch]  (hi),  out[((H/2 * WP + q) * KC + chunk) * out_plane + patch]  (lo)
+// Patch is the fastest index of a thread block so that the writes of fc1's planes are coalesced.
+template <int H, int WP, int KC>
+__global__ void __launch_bounds__(256) cnn_tc_pool_rows(const uint4 *__restrict__ in, long long in_plane, int n_patches,
+                                                        uint4 *__restrict__ out, long long out_plane)
 {
-    constexpr int OW = W / 2;
+    constexpr int OH = H / 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n_patches * OW * OW * KC;
-    if (idx >= total) return;
-    // TO_FC: patch fastest (coalesced writes of fc1's planes); otherwise output pixel fastest
-    int patch, oy, ox, c;
-    if (TO_FC) {
-        patch = (int)(idx % n_patches);
-        long long t = idx / n_patches;
-        c = (int)(t % KC); t /= KC;
-        ox = (int)(t % OW); oy = (int)(t / OW);
-    } else {
-        long long t = idx;
-        ox = (int)(t % OW); t /= OW;
-        oy = (int)(t % OW); t /= OW;
-        patch = (int)(t % n_patches);
-        c = (int)(t / n_patches);
-    }
-    const long long ip = (long long)patch * W * W + (2 * oy) * W + 2 * ox;
+    if (idx >= (long long)n_patches * OH * WP * KC) return;
+    const int patch = (int)(idx % n_patches);
+    long long t = idx / n_patches;
+    const int c = (int)(t % KC); t /= KC;
+    const int ox = (int)(t % WP), oy = (int)(t / WP);
+    const long long ip = (long long)patch * (H * WP) + (2 * oy) * WP + ox;
     const uint4 *ph = in + (long long)c * in_plane + ip, *pl = in + (long long)(KC + c) * in_plane + ip;
     float m[8], v[8];
     unpack8(__ldg(ph), __ldg(pl), m);
-    unpack8(__ldg(ph + 1), __ldg(pl + 1), v);
-#pragma unroll
-    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
-    unpack8(__ldg(ph + W), __ldg(pl + W), v);
-#pragma unroll
-    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
-    unpack8(__ldg(ph + W + 1), __ldg(pl + W + 1), v);
+    unpack8(__ldg(ph + WP), __ldg(pl + WP), v);
 #pragma unroll
     for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
     uint4 hi, lo;
     split8(m, hi, lo);
-    if (TO_FC) {
-        const int q = oy * OW + ox;
-        out[((long long)q * KC + c) * out_plane + patch] = hi;
-        out[((long long)(OW * OW + q) * KC + c) * out_plane + patch] = lo;
-    } else {
-        const long long op = (long long)patch * OW * OW + oy * OW + ox;
-        out[(long long)c * out_plane + op] = hi;
-        out[(long long)(KC + c) * out_plane + op] = lo;
-    }
+    const int q = oy * WP + ox;
+    out[((long long)q * KC + c) * out_plane + patch] = hi;
+    out[((long long)(OH * WP + q) * KC + c) * out_plane + patch] = lo;
 }
 
 // test aid: planes [2][KC][plane] -> dense float32 [pixel][C]
@@ -534,7 +519,7 @@ static TcWork tc_work_layout(int nf, bool dump_a1)
     w.a1_plane = dump_a1 ? plane_units(P * 1296, 0) : 0;
     w.p2_plane = plane_units(P * 256, Derived<Conv3Cfg>::HALO);
     w.a3_plane = plane_units(P * 196, Derived<Conv4Cfg>::HALO);
-    w.a4_plane = plane_units(P * 144, 0);
+    w.a4_plane = plane_units(P * 72, 0);          // conv4 output after the horizontal half of the pooling: 12 x 6
     w.p4_plane = plane_units(P, 0);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
@@ -599,7 +584,7 @@ static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t
                                   (long long)P * 256, P, st));
     TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
                                   (long long)P * 196, P, st));
-    cnn_tc_pool<12, 12, true><<<(unsigned)(((long long)P * 36 * 12 + 255) / 256), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
+    cnn_tc_pool_rows<12, 6, 12><<<(unsigned)(((long long)P * 36 * 12 + 255) / 256), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
     CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool4");
     TC_TRY(launch_layer<Fc1Cfg>(ctx, "cnn_tc_fc1", p4, W.p4_plane, B.off_w[4], B.off_b[4], nullptr, 0, f5, P, P, st));
     return ckb_launch_fc2_decode(ctx, f5, nf, work + W.tmp, d_softmax, d_stones, d_conf, d_keep, st);
