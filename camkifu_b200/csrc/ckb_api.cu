@@ -107,6 +107,7 @@ extern "C" int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, i
                                  size_t d_frame_pitch, void *stream)
 {
     if (!ctx) return CKB_E_INVALID;
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!h_frames || !d_frames || n < 0 || H < 1 || W < 1) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: bad argument");
     int y0 = 0, y1 = H, x0 = 0, x1 = W;
     if (roi4) { y0 = roi4[0]; y1 = roi4[1]; x0 = roi4[2]; x1 = roi4[3]; }
@@ -202,6 +203,7 @@ extern "C" int ckb_warp(ckb_ctx *ctx, const uint8_t *d_frames, int n, int H, int
                         size_t frame_pitch, const double *h_mtx, int n_mtx, uint8_t *d_goban, void *stream)
 {
     if (!ctx) return CKB_E_INVALID;
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!d_frames || !d_goban || !h_mtx || n < 0 || H < 1 || W < 1) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_warp: bad argument");
     if (n_mtx != 1 && n_mtx != n) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_warp: n_mtx must be 1 or n");
     if (row_pitch < (size_t)W * 3 || (n > 1 && frame_pitch < row_pitch * (size_t)H))
@@ -223,6 +225,7 @@ extern "C" int ckb_accumulate(ckb_ctx *ctx, const uint8_t *d_goban, int n, float
                               float *d_snapshots, int snap_every, int snap_phase, void *stream)
 {
     if (!ctx) return CKB_E_INVALID;
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!d_goban || !d_accu || n < 0 || snap_phase < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_accumulate: bad argument");
     if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));

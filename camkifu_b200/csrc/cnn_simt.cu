@@ -286,6 +286,7 @@ extern "C" int ckb_cnn_forward_simt(ckb_ctx *ctx, const uint8_t *d_goban, int n,
 {
     if (!ctx) return CKB_E_INVALID;
     if (!ctx->cnn) CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_forward_simt: call ckb_set_cnn_weights first");
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!d_goban || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward_simt: bad argument");
     if (work_bytes < ckb_cnn_simt_workspace(n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_cnn_forward_simt: workspace too small");
     if (n == 0) return CKB_OK;

@@ -595,6 +595,7 @@ extern "C" int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void
 {
     if (!ctx) return CKB_E_INVALID;
     if (!ctx->cnn || !ctx->cnn->d_tc) CKB_FAIL(ctx, CKB_E_STATE, "ckb_cnn_forward: call ckb_set_cnn_weights first");
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!d_goban || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward: bad argument");
     if (work_bytes < ckb_cnn_workspace(ctx, n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_cnn_forward: workspace too small");
     if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_forward: workspace must be 256-byte aligned");

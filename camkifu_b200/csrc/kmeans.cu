@@ -699,6 +699,7 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
 {
     if (!ctx) return CKB_E_INVALID;
     const int g = ctx->gsize;
+    if (n == 0) return CKB_OK;   // an empty batch is a no-op, whatever the pointers
     if (!d_imgs || !d_rng_states || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: bad argument");
     if (rs < 0 || cs < 0 || re > g || ce > g || rs >= re || cs >= ce)
         CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: region [%d,%d)x[%d,%d) outside the %dx%d goban", rs, re, cs, ce, g, g);
