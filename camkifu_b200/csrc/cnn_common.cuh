@@ -46,6 +46,7 @@ __host__ __device__ __forceinline__ int cnn_patch_origin(int i) { return i < 9 ?
 int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *h_params);   // cnn_tc.cu
 void ckb_cnn_tc_free(ckb_ctx *ctx);
 int ckb_cnn_front_init(ckb_ctx *ctx);                       // cnn_tc_front.cu
+int ckb_cnn_tail_init(ckb_ctx *ctx);                        // cnn_simt.cu
 int ckb_launch_cnn_front(ckb_ctx *ctx, const uint8_t *d_goban, int n_patches, const void *w1, const float *b1, const void *w2,
                          const float *b2, void *p2, long long p2_plane, void *dbg_a1, long long a1_plane, cudaStream_t st);
 int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softmax_or_null, float *d_softmax_tmp,

@@ -248,6 +248,12 @@ __global__ void __launch_bounds__(FC2_THREADS) cnn_fc2_softmax_label(const float
     }
 }
 
+int ckb_cnn_tail_init(ckb_ctx *ctx)   // per context (= per device), called when the weights are installed
+{
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_fc2_softmax_label, cudaFuncAttributeMaxDynamicSharedMemorySize, FC2_SMEM));
+    return CKB_OK;
+}
+
 // d_tmp: n*100*(81 + 2) floats (softmax when the caller does not want it, labels, confidences)
 int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, float *d_softmax, uint8_t *d_stones,
                           float *d_conf, uint8_t *d_keep, cudaStream_t st)
@@ -257,11 +263,6 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
     float *sm = d_softmax ? d_softmax : (float *)d_tmp;
     int *lab = (int *)((float *)d_tmp + (size_t)P * CNN_F6);
     float *cf = (float *)(lab + P);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_fc2_softmax_label, cudaFuncAttributeMaxDynamicSharedMemorySize, FC2_SMEM));
-        attr_set = true;
-    }
     const int per_block = FC2_THREADS / 32;
     int grid = (P + per_block - 1) / per_block;
     if (grid > 2 * ctx->num_sms) grid = 2 * ctx->num_sms;

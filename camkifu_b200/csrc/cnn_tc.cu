@@ -1,7 +1,10 @@
 // K4 — forward pass of the SfNeural CNN on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
 // Replaces NNCache.predict_all_stones = 100 x (NNManager._get_x + net.predict) (src/camkifu/stone/nn_cache.py:25-52)
-// for the network of NNManager.create_net (nn_manager.py:277-298).
+// for the network of NNManager.create_net (nn_manager.py:277-298). This file holds the host side (weight packing,
+// workspace, the layer sequence) and the generic layer kernel that runs conv3, conv4 and fc1; the patch gather, conv1,
+// conv2 and the first max-pool are one fused kernel of their own (cnn_tc_front.cu), the tail (fc2, softmax, decode) is
+// in cnn_simt.cu.
 //
 // Formulation. Every layer is a "shifted GEMM" over a flat list of pixels. Activations live in HBM as channel-chunk
 // planes [plane hi|lo][chunk of 8 channels][pixel][8 x bf16]: a pixel's 8 channels are one 16-byte unit, and consecutive
@@ -17,8 +20,8 @@
 // Precision. Inputs are raw 0..255 and the parity bar on the softmax is 1e-3 relative, which single-pass bf16 or tf32
 // operands miss by 1-2 orders of magnitude. Each float32 operand is therefore split into bf16 hi + lo
 // and three tensor-core products are accumulated in float32:  A_hi W_hi + A_hi W_lo + A_lo W_hi  (the uint8 network
-// input is exact in bf16, so conv1 needs two). Narrow layers (N = 32) put W_hi | W_lo side by side in the B operand so
-// that A_hi is read from shared memory once for both (the MMA is shared-memory bound at N = 32).
+// input is exact in bf16, so conv1 needs two). W_hi | W_lo sit side by side in the B operand so that A_hi is read from
+// shared memory once for both (an M = 128, K = 16 MMA retires every max(N/2, 32 + N/4) cycles: tools/mma_probe.cu).
 //
 // Kernel structure (one persistent CTA per SM, 320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
 // issuer (single thread), warps 2-9 = epilogue (tcgen05.ld -> bias, ReLU, hi/lo split -> coalesced 16-byte stores).
@@ -42,7 +45,7 @@ struct Conv1Cfg {   // input: 16-channel "row window" expansion of the patch (k 
     static constexpr int KCS = 2, NSTAGE = 1, NABUF = 6, NACC = 4;   // tiny tiles: latency bound without depth
     __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
 };
-struct Conv2Cfg {
+struct Conv2Cfg {   // geometry only (weights size): conv1 and conv2 run in cnn_tc_front.cu, not through cnn_tc_layer
     static constexpr int NTAPS = 25, GW = 36, HW_IN = 1296, OH = 32, OW = 32, KC = 4, N = 32, A_PLANES = 2;
     static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 2, NACC = 2;
@@ -492,6 +495,8 @@ int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv3Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv3Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4Cfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Fc1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Fc1Cfg>::SMEM));
+    const int rc = ckb_cnn_tail_init(ctx);
+    if (rc != CKB_OK) return rc;
     return ckb_cnn_front_init(ctx);
 }
 
