@@ -20,14 +20,17 @@
 // One tile = 16 x 16 conv2 outputs of one patch. Per tile:
 //   workers  : read the 24 x 24 raw uint8 window of the canonical image and expand it to conv1's A operand X
 //              (per pixel the 5-pixel row window, k = dx*3 + c, 16 bf16 = two 16-byte chunks)          -> smem X
-//   tensor   : conv1 = 5 vertical taps x 4 M-tiles of 128 window pixels x (W1_hi, W1_lo), N = 32       -> TMEM D1
+//   tensor   : conv1 = 5 vertical taps x 4 M-tiles of 128 window pixels, B = [W1_hi | W1_lo] (N = 64)   -> TMEM D1
 //   workers  : D1 -> +bias, ReLU, bf16 hi/lo split -> conv2's A tile [plane][row 20][parity][10][16 B] -> smem A
 //   tensor   : conv2 = 5 dy x 6 positions x 2 K-steps x (A_hi, A_lo) as above                         -> TMEM D2
 //   workers  : D2 -> hi + lo + correction columns, +bias, ReLU, 2x2 max (in-thread across the pair, one warp shuffle
 //              across rows), hi/lo split -> pooled planes in HBM (conv3's input)
-// Warp 0 issues all MMAs (one elected thread); warps 1-8 are the workers (two per TMEM lane quarter). The A tile and
-// D2 are double buffered; X and D1 are single buffers (conv1 of tile i+1 is issued ahead of conv2 of tile i, so its
-// operands are rebuilt while conv2 of tile i-1 runs). TMEM: D2 = 2 x 192 columns, D1 = 4 x 32.
+// Warp 0 issues all MMAs (one elected thread); warps 1-8 are the workers (two per TMEM lane quarter). The tensor pipe
+// executes conv1(0) | conv1(1) conv2(0) | conv1(2) conv2(1) | ...: conv1 of tile i+1 sits between conv2 of tiles i-1
+// and i, which is when the workers drain D2 of tile i-1 (they release it as soon as their tcgen05.ld have completed) -
+// so one D2 accumulator suffices and TMEM holds D2 = 192 columns + D1 = 4 x 64. The A tile is double buffered
+// (epilogue 1 of tile i+1 writes while conv2 of tile i reads); X and D1 are single buffers, rebuilt / drained while a
+// conv2 runs.
 // Precision: bf16 hi/lo operand split, fp32 accumulation; conv1's uint8 input is exact in bf16.
 #include <cuda_bf16.h>
 
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
     uint64_t *bars = (uint64_t *)(sW2 + FR_W2);
     const uint32_t b_xfull = smem_u32(bars + 0), b_xempty = smem_u32(bars + 1), b_d1full = smem_u32(bars + 2),
                    b_d1empty = smem_u32(bars + 3), b_afull = smem_u32(bars + 4), b_aempty = smem_u32(bars + 6),
-                   b_d2full = smem_u32(bars + 8), b_d2empty = smem_u32(bars + 10), b_wfull = smem_u32(bars + 12);
+                   b_d2full = smem_u32(bars + 8), b_d2empty = smem_u32(bars + 10), b_wfull = smem_u32(bars + 12);   // (one D2)
     uint32_t *tmem_slot = (uint32_t *)(bars + 13);
     const int warp = warp_index(), lane = threadIdx.x & 31;
     const int n_my = (args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -83,8 +86,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
         mbar_init(b_d1full, 1);           mbar_init(b_d1empty, FR_WORKERS);
         for (int i = 0; i < 2; i++) {
             mbar_init(b_afull + 8 * i, FR_WORKERS);  mbar_init(b_aempty + 8 * i, 1);
-            mbar_init(b_d2full + 8 * i, 1);          mbar_init(b_d2empty + 8 * i, FR_WORKERS);
         }
+        mbar_init(b_d2full, 1);           mbar_init(b_d2empty, FR_WORKERS);
         mbar_init(b_wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t D1_COL = 384;     // D2 accumulators: columns [0, 192) and [192, 384); D1: [384, 512) = 4 x 32
+    constexpr uint32_t D1_COL = 192;     // D2 accumulator: columns [0, 192); D1: [192, 448) = 4 M-tiles x (hi 32 | lo 32)
 
     if (warp == 0) {
         // ================================================================= MMA issuer (+ one-off weight load by TMA)
@@ -117,12 +120,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                    for (int dy = 0; dy < 5; dy++) {
-                        const uint64_t da = desc64(x_lo + (uint32_t)(mt * 128 + dy * 20), HI128);
-                        const uint32_t wb = w1_lo + (uint32_t)((dy * 2 * 64 * 16) >> 4);
-                        tc_mma_bf16(tmem_base + D1_COL + mt * 32, da, desc64(wb, HI128), IDESC32, dy != 0);             // W1_hi
-                        tc_mma_bf16(tmem_base + D1_COL + mt * 32, da, desc64(wb + (uint32_t)((32 * 16) >> 4), HI128), IDESC32, 1);   // W1_lo
-                    }
+                    for (int dy = 0; dy < 5; dy++)
+                        tc_mma_bf16(tmem_base + D1_COL + mt * 64, desc64(x_lo + (uint32_t)(mt * 128 + dy * 20), HI128),
+                                    desc64(w1_lo + (uint32_t)((dy * 2 * 64 * 16) >> 4), HI128), IDESC64, dy != 0);
                 tc_commit(b_xempty);
                 tc_commit(b_d1full);
             };
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
                 const int b = i & 1, k = i >> 1;
                 mbar_wait(b_afull + 8 * b, k & 1);          // epilogue 1 of tile i is done: D1 and X are free again
                 if (i + 1 < n_my) conv1(i + 1);
-                mbar_wait(b_d2empty + 8 * b, (k & 1) ^ 1);
+                mbar_wait(b_d2empty, (i & 1) ^ 1);          // the workers have read D2 of tile i-1
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + b * 192;
+                const uint32_t d_tmem = tmem_base;
                 const uint32_t a_lo = desc_lo(smem_u32(sA + b * FR_ATILE), FR_APLANE);
 #pragma unroll
                 for (int dy = 0; dy < 5; dy++) {
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
                     }
                 }
                 tc_commit(b_aempty + 8 * b);
-                tc_commit(b_d2full + 8 * b);
+                tc_commit(b_d2full);
             }
         }
     } else {
@@ -220,17 +220,18 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
                 const int m = mt * 128 + q * 32 + lane;      // window pixel (wy, wx) = (m / 20, m % 20), 400 valid
                 const int wy = m / 20, wx = m - wy * 20;
                 const uint32_t aoff = wy * FR_ROWPITCH + (wx & 1) * FR_PARITY + (wx >> 1) * 16;
-                const uint32_t taddr = lane_base + D1_COL + mt * 32;
+                const uint32_t taddr = lane_base + D1_COL + mt * 64;
 #pragma unroll
                 for (int c2 = 0; c2 < 2; c2++) {
                     const int cc = 2 * half + c2;
-                    float v[8];
+                    float v[8], u[8];
                     tc_ld8(taddr + 8 * cc, v);
+                    tc_ld8(taddr + 32 + 8 * cc, u);
                     tc_ld_wait();
                     const float4 b0 = __ldg((const float4 *)args.b1 + 2 * cc), b1 = __ldg((const float4 *)args.b1 + 2 * cc + 1);
                     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j] + bb[j], 0.f);
+                    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j] + u[j] + bb[j], 0.f);
                     uint4 hi, lo;
                     split8(v, hi, lo);
                     if (m < 400) {
@@ -258,31 +259,37 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
         // MMA row m = 8 * (tile row r) + (pair g): columns [64 j + 16 cc, +16) = W_hi | W_lo parts of output (r, 2g + j),
         // channels 8 cc .. 8 cc + 7; columns [128 + 32 j + 8 cc, +8) = the A_lo W_hi correction.
         auto epilogue2 = [&](int i) {
-            const int b = i & 1, k = i >> 1;
             const int tile = (int)blockIdx.x + i * (int)gridDim.x;
             const int patch = tile >> 2, ty = (tile >> 1) & 1, tx = tile & 1;
             const int r = q * 4 + (lane >> 3), g = lane & 7;
             const bool writer = (lane & 8) == 0;             // even tile row: owns the pooled pixel (r / 2, g)
             const long long opix = (long long)patch * 256 + (8 * ty + (r >> 1)) * 16 + 8 * tx + g;
-            mbar_wait(b_d2full + 8 * b, k & 1);
+            mbar_wait(b_d2full, i & 1);
             tc_fence_after();
-            const uint32_t taddr = lane_base + b * 192;
+            const uint32_t taddr = lane_base;
+            float h0[2][16], h1[2][16], l0[2][8], l1[2][8];
 #pragma unroll
             for (int c2 = 0; c2 < 2; c2++) {
                 const int cc = 2 * half + c2;
-                float h0[16], h1[16], l0[8], l1[8];
-                tc_ld16(taddr + 16 * cc, h0);
-                tc_ld16(taddr + 64 + 16 * cc, h1);
-                tc_ld8(taddr + 128 + 8 * cc, l0);
-                tc_ld8(taddr + 160 + 8 * cc, l1);
-                tc_ld_wait();
+                tc_ld16(taddr + 16 * cc, h0[c2]);
+                tc_ld16(taddr + 64 + 16 * cc, h1[c2]);
+                tc_ld8(taddr + 128 + 8 * cc, l0[c2]);
+                tc_ld8(taddr + 160 + 8 * cc, l1[c2]);
+            }
+            tc_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_d2empty);            // D2 is in registers: conv2 of the next tile may start
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const int cc = 2 * half + c2;
                 const float4 b0 = __ldg((const float4 *)args.b2 + 2 * cc), b1 = __ldg((const float4 *)args.b2 + 2 * cc + 1);
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float x0 = h0[j] + h0[8 + j] + l0[j] + bb[j];
-                    const float x1 = h1[j] + h1[8 + j] + l1[j] + bb[j];
+                    const float x0 = h0[c2][j] + h0[c2][8 + j] + l0[c2][j] + bb[j];
+                    const float x1 = h1[c2][j] + h1[c2][8 + j] + l1[c2][j] + bb[j];
                     float x = fmaxf(fmaxf(x0, x1), 0.f);
                     x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
                     v[j] = x;
@@ -294,9 +301,6 @@ __global__ void __launch_bounds__(FR_THREADS, 1) cnn_tc_front(const __grid_const
                     args.out[(long long)(4 + cc) * args.out_plane + opix] = lo;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_d2empty + 8 * b);
         };
 
         build_x(0);
