@@ -14,8 +14,9 @@ from .engine import StoneEngine, rng_seed, rng_advance
 
 
 def pinned_frames(n: int, H: int, W: int) -> torch.Tensor:
-    """Page-locked host buffer for n BGR frames (what the capture thread should decode into)."""
-    return torch.empty((n, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    """Page-locked host buffer for n BGR frames (what the capture thread should decode into). Without a CUDA device
+    (host-side tests of the ingest code) the buffer is ordinary memory."""
+    return torch.empty((n, H, W, 3), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
 
 
 class DetectPipeline:

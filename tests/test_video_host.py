@@ -1,0 +1,59 @@
+"""Host side of the offline video path (camkifu_b200/video.py): decode thread, pinned ring, frame ranges."""
+import os
+
+import numpy as np
+import pytest
+
+from camkifu_b200 import synth
+
+
+def write_lossless(path, frames):
+    import cv2
+    h, w = frames.shape[1:3]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 30, (w, h))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+
+
+@pytest.fixture(scope="module")
+def clip(tmp_path_factory):
+    frames, mtx, truth, _ = synth.make_clip(21, 23, 120, 160)
+    path = str(tmp_path_factory.mktemp("video") / "clip.avi")
+    write_lossless(path, frames)
+    return path, frames, mtx
+
+
+@pytest.mark.parametrize("rng", [(0, None), (6, 19), (9, 9), (20, 400)])
+def test_frame_source_reads_ranges_bit_exact(clip, rng):
+    from camkifu_b200.video import FrameSource
+    path, frames, _ = clip
+    start, stop = rng
+    src = FrameSource(path, start, stop, batch=4, depth=3)
+    assert (src.n_total, src.H, src.W) == (23, 120, 160)
+    got, pos = [], start
+    for buf, m, first in src:
+        assert first == pos and 1 <= m <= 4
+        got.append(buf[:m].numpy().copy())
+        pos += m
+        src.release(buf)                     # without this the decoder would stall after `depth` batches
+    want = frames[start:min(stop if stop is not None else 23, 23)]
+    assert len(src) == len(want)
+    if len(want):
+        assert np.array_equal(np.concatenate(got), want)
+    else:
+        assert got == []
+
+
+def test_frame_source_array_and_errors(clip):
+    from camkifu_b200.video import FrameSource, open_source
+    _, frames, _ = clip
+    src = FrameSource(frames, 3, 11, batch=5, depth=2)
+    out = []
+    for buf, m, first in src:
+        out.append(buf[:m].numpy().copy())
+        src.release(buf)
+    assert np.array_equal(np.concatenate(out), frames[3:11])
+    with pytest.raises(IOError):
+        open_source(os.path.join(os.path.dirname(__file__), "no_such_video.avi"))
