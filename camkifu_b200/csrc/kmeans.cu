@@ -255,6 +255,60 @@ __device__ void pp_pass(const void *px, int N, int nseg, KmShared &sh, int ncen,
     __syncthreads();
 }
 
+// The same pass for uint8 pixels in integer arithmetic. Pixels and k-means++ centres (which are pixels) are packed
+// bytes, d(x, c) = x.x + c.c - 2 x.c with three dp4a; every float32 / float64 quantity of the float version is an
+// integer below 2^24 / 2^53 here, so the results are identical whatever the summation order.
+template <int NW>
+__device__ void pp_pass_u8(const void *px, int N, int nseg, KmShared &sh, int ncen, int ncand, int warp, int lane)
+{
+    const uint32_t *pw = (const uint32_t *)px;
+    uint32_t cw[3], cc[3], bw[2] = {0u, 0u}, bc[2] = {0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        cw[c] = __ldg(pw + sh.cand[c < ncand ? c : 0]) & 0x00ffffffu;
+        cc[c] = __dp4a(cw[c], cw[c], 0u);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (c < ncen) {
+            bw[c] = (uint32_t)sh.cen[3 * c] | ((uint32_t)sh.cen[3 * c + 1] << 8) | ((uint32_t)sh.cen[3 * c + 2] << 16);
+            bc[c] = __dp4a(bw[c], bw[c], 0u);
+        }
+    }
+    for (int seg = warp; seg < nseg; seg += NW) {
+        uint32_t acc[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < KM_SEG / 32; j++) {
+            const int i = seg * KM_SEG + j * 32 + lane;
+            if (i < N) {
+                const uint32_t x = __ldg(pw + i) & 0x00ffffffu;
+                const uint32_t xx = __dp4a(x, x, 0u);
+                uint32_t base = 0xffffffffu;
+                if (ncen > 0) base = xx + bc[0] - 2u * __dp4a(x, bw[0], 0u);
+                if (ncen > 1) base = min(base, xx + bc[1] - 2u * __dp4a(x, bw[1], 0u));
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    if (c < ncand) acc[c] += min(xx + cc[c] - 2u * __dp4a(x, cw[c], 0u), base);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (c < ncand) {
+                const uint32_t t = __reduce_add_sync(0xffffffffu, acc[c]);   // <= 256 x 195075: fits
+                if (lane == 0) sh.u.segsum[1 + c][seg] = (double)t;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < ncand) {
+        double t = 0.0;
+        for (int s2 = lane; s2 < nseg; s2 += 32) t += sh.u.segsum[1 + warp][s2];
+        t = warp_sum_d(t);
+        if (lane == 0) sh.dtmp[1 + warp] = t;
+    }
+    __syncthreads();
+}
+
 template <bool F32, int NT>
 __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict__ scratch,
                                                                  size_t scratch_stride, int N,
@@ -262,6 +316,12 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
                                                                  KmAttempt *__restrict__ results)
 {
     constexpr int NW = NT / 32;
+    // uint8 input: the labels of the current iteration are kept (1 byte per pixel, behind the packed pixels in this
+    // frame's scratch slot, one array per attempt) so that the compactness pass need not recompute the three distances
+    // (7 N bytes of the 16 S^2-byte slot; the pixel part is only ever read, the label part only by this CTA)
+    uint8_t *lab_cache = F32 ? nullptr
+                             : (uint8_t *)const_cast<void *>(scratch) + (size_t)blockIdx.y * scratch_stride +
+                                   (((size_t)N * 4 + 15) & ~(size_t)15) + (size_t)blockIdx.x * (((size_t)N + 15) & ~(size_t)15);
     __shared__ KmShared sh;
     const int attempt = blockIdx.x, frame = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -276,10 +336,18 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
 #pragma unroll
     for (int k = 0; k < 6; k++) u[k] = rng_double(st);
 
+#ifdef KM_TIMING
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#define KM_TICK(slot) do { const long long t_now = clock64(); tk[slot] += t_now - t_prev; t_prev = t_now; } while (0)
+#else
+#define KM_TICK(slot) do { } while (0)
+#endif
     // ---- k-means++ seeding
     if (tid == 0) { sh.cand[0] = c0; sh.cand[1] = c0; sh.cand[2] = c0; }
     __syncthreads();
-    pp_pass<F32, NW>(px, N, nseg, sh, 0, 1, warp, lane);
+    if (F32) pp_pass<F32, NW>(px, N, nseg, sh, 0, 1, warp, lane);
+    else pp_pass_u8<NW>(px, N, nseg, sh, 0, 1, warp, lane);
     if (tid < 3) {
         const float3 x = load_px<F32>(px, c0);
         sh.cen[tid] = tid == 0 ? x.x : (tid == 1 ? x.y : x.z);
@@ -294,7 +362,8 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
             if (lane == 0) sh.cand[warp] = ci;
         }
         __syncthreads();
-        pp_pass<F32, NW>(px, N, nseg, sh, k, 3, warp, lane);
+        if (F32) pp_pass<F32, NW>(px, N, nseg, sh, k, 3, warp, lane);
+        else pp_pass_u8<NW>(px, N, nseg, sh, k, 3, warp, lane);
         // best trial: strict '<' in trial order
         int best = 0;
         double bs = sh.dtmp[1];
@@ -310,6 +379,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
         __syncthreads();
     }
 
+    KM_TICK(0);   // k-means++
     // ---- Lloyd iterations
     const int nchunk = (N + KM_CH - 1) / KM_CH;
     int iter = 1;  // iteration 0 was the seeding; labels are (conceptually) assigned against sh.cen
@@ -341,6 +411,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
                     if (i < N) {
                         const float3 x = load_px<F32>(px, i);
                         const int lab = argmin3(x, oc);
+                        lab_cache[i] = (uint8_t)lab;
                         const int vx = (int)x.x, vy = (int)x.y, vz = (int)x.z;
                         c0n += lab == 0;
                         c1n += lab == 1;
@@ -361,25 +432,44 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
                 }
             }
             __syncthreads();
+            KM_TICK(1);   // parallel pass
             if (warp == 0) {
-                int first = nchunk, run = 0;
-                if (lane < 9) {
-                    for (int ch = 0; ch < nchunk; ch++) {
-                        run += sh.csum[lane][ch];
-                        if (run > (1 << 24)) { first = ch; break; }   // a partial sum inside chunk ch may need rounding
+                // first chunk in which any of the nine running sums passes 2^24, and the exact sums before it: every
+                // lane owns a run of consecutive chunks, warp scan over the lane totals, one chain after the other
+                const int per = (nchunk + 31) >> 5, c_lo = lane * per, c_hi = min(nchunk, c_lo + per);
+                int first = nchunk;
+#pragma unroll 1
+                for (int c = 0; c < 9; c++) {
+                    int loc = 0;
+                    for (int ch = c_lo; ch < c_hi; ch++) loc += sh.csum[c][ch];
+                    int incl = loc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    if (incl > (1 << 24)) {          // a partial sum inside one of this lane's chunks may need rounding
+                        int run = incl - loc;
+                        for (int ch = c_lo; ch < c_hi; ch++) {
+                            run += sh.csum[c][ch];
+                            if (run > (1 << 24)) { first = min(first, ch); break; }
+                        }
                     }
                 }
                 first = __reduce_min_sync(0xffffffffu, first);
-                run = 0;
-                if (lane < 9) {
-                    for (int ch = 0; ch < first; ch++) run += sh.csum[lane][ch];
-                    sh.sums[lane] = (float)run;                       // exact: run <= 2^24
+#pragma unroll 1
+                for (int c = 0; c < 9; c++) {
+                    int loc = 0;
+                    for (int ch = c_lo; ch < min(c_hi, first); ch++) loc += sh.csum[c][ch];
+                    loc = __reduce_add_sync(0xffffffffu, loc);
+                    if (lane == c) sh.sums[c] = (float)loc;           // exact: loc <= 2^24
                 }
                 if (lane == 0) sh.ch0 = first;
             }
             __syncthreads();
             ch0 = sh.ch0;
             if (warp == 0 && lane < 9) acc = sh.sums[lane];
+            KM_TICK(2);   // prefix over chunk sums
         }
         constexpr int Q = (KM_CH + NT - 1) / NT;     // chunk pixels per thread in the serial phase
         float3 xn[Q];
@@ -428,6 +518,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
             }
             __syncthreads();
         }
+        KM_TICK(3);   // serial chunks
         if (warp == 0 && lane < 9) sh.sums[lane] = acc;
         // counts
         c0n = __reduce_add_sync(0xffffffffu, c0n);
@@ -513,6 +604,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
         if (sh.flag) break;
     }
 
+    KM_TICK(4);   // iteration tails
     // ---- compactness: labels stay those assigned against oldc (+ repairs); distances to the final centres
     {
         float oc[9], nc[9];
@@ -523,7 +615,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
 #pragma unroll 4
         for (int i = tid; i < N; i += NT) {
             const float3 x = load_px<F32>(px, i);
-            int lab = argmin3(x, oc);
+            int lab = F32 ? argmin3(x, oc) : (int)lab_cache[i];
             for (int q = 0; q < n_fix; q++) if (sh.fix_idx[q] == i) lab = sh.fix_k[q];
             const float cx = lab == 0 ? nc[0] : (lab == 1 ? nc[3] : nc[6]);
             const float cy = lab == 0 ? nc[1] : (lab == 1 ? nc[4] : nc[7]);
@@ -544,6 +636,12 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
             r.iters = iter;
         }
     }
+    KM_TICK(5);   // compactness
+#ifdef KM_TIMING
+    if (tid == 0 && frame == 0)
+        printf("attempt %d iters %d: pp %lld  pass1 %lld  prefix %lld  serial %lld  tails %lld  compact %lld cycles\n", attempt,
+               iter, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ zone classification

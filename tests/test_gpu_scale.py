@@ -122,3 +122,26 @@ def test_error_codes(engine):
     L = engine.L
     assert L.ckb_cnn_forward(engine._h, None, 1, None, 0, None, None, None, None, None) != 0
     assert b"bad argument" in L.ckb_last_error(engine._h)
+
+
+@pytest.mark.parametrize("gsize", [9, 13, 19])
+def test_config4_4k_mixed_board_sizes(oracle, gsize):
+    """BASELINE config 4: 3840x2160 frames, boards of 9 / 13 / 19 lines under perspective jitter — the warped pixels, the
+    k-means labels and the board state are bit-identical to the oracle's (one oracle run per board size, as the
+    reference needs one process per gsize)."""
+    from camkifu_b200.engine import StoneEngine, rng_seed, rng_advance
+    S = 20 * gsize
+    eng = StoneEngine(gsize)
+    frames, mtx, truth, _ = synth.make_clip_parallel(40 + gsize, 3, 2160, 3840, gsize=gsize)
+    goban = eng.warp(torch.from_numpy(frames).cuda(), mtx)
+    st0 = rng_seed(gsize)
+    states = [rng_advance(st0, i) for i in range(3)]
+    res = eng.find_stones(goban, states, want=("stones", "trusted", "labels", "centers"))
+    for i in range(3):
+        g_ref = oracle.c_warp(frames[i], mtx, S)
+        assert np.array_equal(goban[i].cpu().numpy(), g_ref)
+        ref = oracle.c_find_stones(g_ref, states[i], gsize, 0, gsize, 0, gsize)
+        assert np.array_equal(res["labels"][i].cpu().numpy(), ref["labels"])
+        assert np.array_equal(res["centers"][i].cpu().numpy(), ref["centers"])
+        assert np.array_equal(res["stones"][i].cpu().numpy(), ref["stones"])
+    assert np.array_equal(res["stones"].cpu().numpy(), truth)
