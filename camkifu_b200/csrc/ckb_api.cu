@@ -115,6 +115,19 @@ extern "C" int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, i
     if (y1 <= y0 || x1 <= x0 || n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t wbytes = (size_t)(x1 - x0) * 3;
+    if (n > 1 && h_frame_pitch % h_row_pitch == 0 && d_frame_pitch % d_row_pitch == 0) {
+        // one pitched 3-D copy for the whole sub-batch: width = ROI row bytes, height = ROI rows, depth = frames
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof p);
+        p.srcPtr = make_cudaPitchedPtr((void *)h_frames, h_row_pitch, (size_t)W * 3, h_frame_pitch / h_row_pitch);
+        p.dstPtr = make_cudaPitchedPtr((void *)d_frames, d_row_pitch, (size_t)W * 3, d_frame_pitch / d_row_pitch);
+        p.srcPos = make_cudaPos((size_t)x0 * 3, (size_t)y0, 0);
+        p.dstPos = make_cudaPos((size_t)x0 * 3, (size_t)y0, 0);
+        p.extent = make_cudaExtent(wbytes, (size_t)(y1 - y0), (size_t)n);
+        p.kind = cudaMemcpyHostToDevice;
+        CKB_CUDA(ctx, cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
+        return CKB_OK;
+    }
     for (int i = 0; i < n; i++) {
         const uint8_t *src = h_frames + (size_t)i * h_frame_pitch + (size_t)y0 * h_row_pitch + (size_t)x0 * 3;
         uint8_t *dst = d_frames + (size_t)i * d_frame_pitch + (size_t)y0 * d_row_pitch + (size_t)x0 * 3;
