@@ -183,3 +183,22 @@ def make_game_clip(seed: int, n: int, H: int, W: int, events=(), gsize: int = 19
         frames[i] = np.clip(frame, 0, 255).astype(np.uint8)
         truth[i] = stones
     return frames, mtx, truth, corners
+
+
+def wild_homographies(rng, n):
+    """Homographies far from a board finder's: the horizon inside the canonical square (the projective denominator
+    changes sign), singular matrices (cv::invert yields zeros), scales that saturate the fixed-point coordinates,
+    random dense matrices."""
+    out = []
+    for t in range(n):
+        kind = t % 4
+        if kind == 0:
+            M = np.array([[1.0, 0.1, 5], [0.05, 1.2, -3], [rng.normal(0, 4e-3), rng.normal(0, 4e-3), 1.0]])
+        elif kind == 1:
+            M = np.array([[1.0, 2, 3], [2, 4, 6], [0.5, 1, 1.5]]) * rng.normal()
+        elif kind == 2:
+            M = np.diag([1e-4, 1e-4, 1.0]) @ np.array([[1, 0.2, 0], [0.1, 1, 0], [0, 0, 1.0]])
+        else:
+            M = rng.normal(size=(3, 3)) * np.array([[1, 1, 100], [1, 1, 100], [1e-3, 1e-3, 1]])
+        out.append(M)
+    return out

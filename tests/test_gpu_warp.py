@@ -41,6 +41,18 @@ def test_warp_bit_exact_vs_oracle(engine, oracle, H, W):
         assert np.array_equal(out1[k], oracle.c_warp(frames[k], mats[0], 380))
 
 
+def test_warp_wild_homographies(engine, oracle):
+    """Horizon inside the canonical square, singular matrices, saturating scales, random dense matrices: still the
+    oracle's bits (which are cv2's: tests/test_oracle_vs_cv2.py::test_warp_wild_homographies_bit_exact)."""
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, (240, 320, 3), dtype=np.uint8)
+    mats = synth.wild_homographies(rng, 24)
+    frames = torch.from_numpy(np.stack([src] * len(mats))).cuda()
+    out = engine.warp(frames, np.array(mats)).cpu().numpy()
+    for k, M in enumerate(mats):
+        assert np.array_equal(out[k], oracle.c_warp(src, M, 380)), "homography %d" % k
+
+
 def test_warp_pitched_view_and_many_frames(engine, oracle):
     rng = np.random.default_rng(3)
     big = rng.integers(0, 256, (40, 300, 420, 3), dtype=np.uint8)

@@ -20,6 +20,13 @@ def test_invert_and_warp_bit_exact(oracle):
         assert np.array_equal(cv2.warpPerspective(src, M, (S, S)), oracle.c_warp(src, M, S))
 
 
+def test_warp_wild_homographies_bit_exact(oracle):
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, (240, 320, 3), dtype=np.uint8)
+    for M in synth.wild_homographies(rng, 24):
+        assert np.array_equal(cv2.warpPerspective(src, M, (380, 380)), oracle.c_warp(src, M, 380))
+
+
 def test_accumulate_weighted_bit_exact(oracle):
     rng = np.random.default_rng(1)
     a = rng.integers(0, 256, (380, 380, 3), dtype=np.uint8).astype(np.float32)
