@@ -164,6 +164,8 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from camkifu_b200.affinity import bind_to_gpu
+    numa_bound = bind_to_gpu(local_rank) if world > 1 else False   # pinned staging buffers on the GPU's own NUMA node
     eng = StoneEngine(GSIZE, device=dev)
     params = weights.glorot_params(seed=0)
     eng.set_cnn_weights(params)
@@ -275,9 +277,15 @@ def run_b200(args, rank, world, local_rank):
     cnn_flop = 2.0 * sum(CNN_MAC_PER_PATCH.values()) * 100 * BATCH
     cnn_ms = sum(v[0] for n, v in agg.items() if n.startswith("cnn_")) / args.steps
 
-    # ---- CPU baseline on this host (bounded sample)
+    # ---- CPU baseline on this host (bounded sample; rank 0 of the N = 1 run only)
     threads = os.cpu_count() or 1
-    cpu_fps, cpu_n = cpu_reference_fps(frames_np, mtx, params, threads, budget_s=15.0, max_frames=64)
+    if world == 1:
+        cpu_fps, cpu_n = cpu_reference_fps(frames_np, mtx, params, threads, budget_s=15.0, max_frames=64)
+        cpu_line = {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "%d frames of the same clip: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "
+                              "for Keras predict, one 100-patch batch per frame) + decode" % cpu_n}
+    else:
+        cpu_line = None      # timed at N = 1 (see the N = 1 line / --impl reference)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
@@ -285,14 +293,13 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "frame": [H, W], "gsize": GSIZE, "frames_per_step_per_gpu": BATCH,
                        "weights": "glorot_uniform seed 0 (reference architecture, nn_manager.py:277-298)",
                        "l2": "inputs larger than L2: two resident 398 MB batches used alternately",
-                       "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world},
+                       "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world,
+                       "numa_bound": numa_bound},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "camkifu_b200.pipeline.DetectPipeline.detect_stream (pinned host frames, ROI upload, 16-frame "
                            "sub-batches double buffered, results of every batch read back to the host)", "matches_resident_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d frames of the same clip: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "
-                                       "for Keras predict, one 100-patch batch per frame) + decode" % cpu_n},
+            "cpu_baseline": cpu_line,
             "kernels": [{"name": n, "ms": round(ms, 4), "launches_per_step": c / args.steps,
                          "share": round(ms * c / ksum, 4)} for n, ms, c in kern],
             "cnn": {"tflops_algorithmic": cnn_flop / (cnn_ms * 1e-3) / 1e12, "ms_per_step": cnn_ms},
