@@ -17,10 +17,11 @@ The reference cannot travel to the GPU box, so its outputs on seeded synthetic i
                            clip (a hand places two stones): the MOG2 foreground masks of _learn_bg
                            (stonesfinder.py:113-115,171-176) and the per-zone foreground sums is_agitated reduces them to
                            (sf_neural.py:178-180)
-  neural_stream.npz        the unmodified SfNeural._find over 48 frames of such a clip (background sampling, initial
+  neural_stream.npz        the unmodified SfNeural._find over 72 frames of such a clip (background sampling, initial
                            assessment, mark_targets / select_targets / process_targets / lookback, sf_neural.py:36-176)
-                           with `net.predict` = the oracle's float32 forward on seeded Glorot weights: every instruction
-                           piped to the controller, per frame, plus the targets / heat-map state
+                           with `net.predict` = the oracle's float32 forward on the trained fixture weights
+                           (sfneural_trained.npz, oracle/train_fixture.py): every instruction piped to the controller,
+                           per frame, plus the targets / heat-map state
 """
 import os
 import subprocess
@@ -226,7 +227,8 @@ def gen_neural_stream():
     from camkifu.stone.nn_manager import NNManager
     import camkifu.stone.sf_neural as sfn
 
-    params = weights.glorot_params(seed=0)
+    # realistic weights (oracle/train_fixture.py): the stream then carries real moves and peaked softmax outputs
+    params = np.load(os.path.join(GOLD, "sfneural_trained.npz"))["params"]
     margins = []
 
     class OracleNet:                    # stands in for the Keras model: float32 forward of the same architecture
@@ -237,7 +239,7 @@ def gen_neural_stream():
             return y
 
     NNManager._network = OracleNet()
-    n = 48
+    n = 72
     frames, mtx, truth, _ = synth.make_game_clip(int(os.environ.get("CKB_NS_SEED", "11")), n, 120, 160, events=NEURAL_EVENTS)
     vm = refimport.FakeVManager(mtx)
     sf = sfn.SfNeural(vm)

@@ -99,3 +99,22 @@ def test_tc_matches_simt_on_noise(engine):
     b = engine.cnn_forward(goban, simt=True)["softmax"].cpu().numpy()
     err = np.abs(a - b).max(axis=2) / b.max(axis=2)
     assert err.max() <= SOFTMAX_RTOL, "softmax error %.3g" % err.max()
+
+
+def test_tc_forward_trained_weights(oracle, golden):
+    """Realistic weights (tests/golden/sfneural_trained.npz: the reference architecture trained on synthetic boards by
+    oracle/train_fixture.py — the reference's own model does not ship): peaked softmax outputs, large logits. Same bar:
+    1e-3 relative on the softmax, identical labels and decode; and the network reads the synthetic boards correctly."""
+    import cv2
+    from camkifu_b200.engine import StoneEngine
+    params = golden("sfneural_trained.npz")["params"]
+    eng = StoneEngine(19)
+    eng.set_cnn_weights(params)
+    frames, M, truth, _ = synth.make_clip(12, 3, 360, 480)
+    goban = np.stack([cv2.warpPerspective(f, M, (380, 380)) for f in frames])
+    out = eng.cnn_forward(torch.from_numpy(goban).cuda())
+    check(out, goban, oracle, params)
+    assert np.array_equal(out["stones"].cpu().numpy(), truth)
+    assert float(out["conf"].min()) > 0.9
+    simt = eng.cnn_forward(torch.from_numpy(goban).cuda(), simt=True)
+    assert np.array_equal(simt["stones"].cpu().numpy(), truth)

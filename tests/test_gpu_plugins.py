@@ -144,14 +144,16 @@ def test_detect_stream_matches_synchronous_calls():
 
 
 def test_sfneural_stream_matches_reference(golden):
-    """neural_stream.npz: the unmodified SfNeural._find over a 48-frame 'game' clip (background sampling, initial
-    assessment, foreground-driven targeting, look-back), with net.predict = the oracle's float32 forward. The plugin —
-    MOG2 and the CNN on the device — must send the controller the same stone updates on the same frames, and carry the
-    same targets / heat-map state. (Within one frame the reference iterates a Python set: order is not defined.)"""
+    """neural_stream.npz: the unmodified SfNeural._find over a 72-frame 'game' clip (background sampling, initial
+    assessment, foreground-driven targeting, look-back), with net.predict = the oracle's float32 forward on the trained
+    fixture weights. The plugin — MOG2 and the CNN on the device — must send the controller the same stone updates on the
+    same frames (the initial assessment, the look-back cancellations, the three stones a hand plays during the clip),
+    and carry the same targets / heat-map state. (Within one frame the reference iterates a Python set: order is not
+    defined.)"""
     g = golden("neural_stream.npz")
     frames, mtx, log = g["frames"], g["mtx"], g["log"]
     vm = HeadlessVManager(mtx)
-    plugins.SfNeuralB200.cnn_params = weights.glorot_params(seed=0)
+    plugins.SfNeuralB200.cnn_params = golden("sfneural_trained.npz")["params"]
     try:
         sf = plugins.SfNeuralB200(vm)
         sf.bg_init_frames = int(g["bg_init_frames"])
@@ -176,6 +178,9 @@ def test_sfneural_stream_matches_reference(golden):
         plugins.SfNeuralB200.cnn_params = None
     assert np.array_equal(codes(vm.controller.stones), g["board"])
     assert len(log) > 100 and g["targets"].max() > plugins.TARGET_THRESH     # the clip exercised the steady state
+    assert (log[:, 1] == 1).sum() == 3                                       # three stones were suggested one by one
+    for (_, color, r, c) in g["events"]:
+        assert codes(vm.controller.stones)[r, c] == color                    # ... the ones the hand played
 
 
 def test_process_video_file_sharded(tmp_path):

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--clips", type=int, default=3)
     ap.add_argument("--weights", default=None)
+    ap.add_argument("--bg-init-frames", type=int, default=None, dest="bg_init_frames")
     args = ap.parse_args()
     reports = []
     for k in range(args.clips):
@@ -44,8 +45,13 @@ def main():
         vm = HeadlessVManager(mtx, video="synthetic_%d.avi" % k)
         cls = getattr(plugins, args.sf)
         if args.sf == "SfNeuralB200":
-            cls.cnn_params = np.load(args.weights) if args.weights else weights.glorot_params(seed=0)
+            if args.weights and args.weights.endswith(".npz"):
+                cls.cnn_params = np.load(args.weights)["params"]
+            else:
+                cls.cnn_params = np.load(args.weights) if args.weights else weights.glorot_params(seed=0)
         sf = cls(vm)
+        if args.bg_init_frames is not None and hasattr(sf, "bg_init_frames"):
+            sf.bg_init_frames = args.bg_init_frames
         if hasattr(sf, "set_rng_seed"):
             sf.set_rng_seed(k)
         t0 = time.time()
@@ -56,8 +62,10 @@ def main():
         board = np.vectorize(CODE.get)(ctl.stones).astype(np.uint8)
         region = (slice(None), slice(6, 13)) if args.sf == "SfClusteringB200" else (slice(None), slice(None))
         match = float((board[region] == truth[-1][region]).mean())   # SfClustering._find looks at columns 6..12 only
-        reports.append("[synthetic_%d: %.1f%% in %.1f s; %.0f frames/s after start-up]"
-                       % (k, 100 * match, dt, (args.frames - 2) / steady))
+        new = [(r, c) for (_, _, r, c) in events]
+        found = sum(int(board[r, c] == truth[-1][r, c]) for r, c in new)
+        reports.append("[synthetic_%d: %.1f%% in %.1f s; %.0f frames/s after start-up; %d of %d stones played during the "
+                       "clip detected]" % (k, 100 * match, dt, (args.frames - 2) / steady, found, len(new)))
         print(reports[-1], flush=True)
     return 0
 
