@@ -60,7 +60,7 @@ struct Conv3Cfg {
 struct Conv4Cfg {   // POOL_X: the epilogue already takes the horizontal half of the 2x2 max-pool that follows
     static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
     static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false, POOL_X = true;
-    static constexpr int KCS = 6, NSTAGE = 4, NABUF = 2, NACC = 2;
+    static constexpr int KCS = 4, NSTAGE = 8, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
 };
 struct Fc1Cfg {     // "pixels" are patches; tap q = pooled pixel, its A tile is streamed with its weights
