@@ -67,6 +67,8 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)            # first queries are slow: pay for
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)             # them outside the timed region
             self.ok = True
         except Exception:
             self.ok = False
