@@ -249,7 +249,8 @@ def build_classes(Base):
         (the reference draws from cv2's process-global generator; here the finder owns it — see set_rng_seed)."""
 
         def __init__(self, vmanager):
-            super().__init__(vmanager, learn_bg=False)   # MOG2 is not used by this finder's detection
+            super().__init__(vmanager, learn_bg=False)   # no cv2 model: like every finder of the reference this one
+            self._enable_bg()                            # keeps a background model (get_foreground), here on the device
             self._d_accu = None
             self._has_accu = False
             self.rng_state = None

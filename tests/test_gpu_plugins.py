@@ -215,3 +215,19 @@ def test_process_video_file_sharded(tmp_path):
     # an in-memory array is a valid source too
     mem = process_video(frames, mtx, mode="neural", batch=16, engine=eng)
     assert np.array_equal(mem["stones"], whole["stones"])
+
+
+def test_sfclustering_keeps_a_background_model(golden):
+    """Like the reference's SfClustering (StonesFinder.__init__ default learn_bg=True), the plugin maintains the MOG2
+    model on every frame: get_foreground() returns the mask cv2 would have produced, bg_init_frames exists."""
+    g = golden("background_stream.npz")
+    vm = HeadlessVManager(g["mtx"])
+    sf = plugins.SfClusteringB200(vm)
+    assert sf.bg_init_frames == 50
+    sf.bg_init_frames = int(g["bg_init_frames"])
+    for i in range(12):
+        sf._doframe(g["frames"][i].copy())
+        sf.total_f_processed += 1
+        fg = sf.get_foreground()
+        assert fg.shape == (380, 380) and np.array_equal(np.packbits(fg > 0), g["masks"][i]), "frame %d" % i
+    assert sf.is_agitated(*np.unravel_index(int(g["zone_fg"][11].argmax()), (19, 19)))
