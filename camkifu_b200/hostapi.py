@@ -36,13 +36,25 @@ CODE_TO_COLOR = (E, B, W)          # uint8 codes of the C ABI -> the Golib colou
 canonical_size = 20 * gsize        # cvconf.py:10
 
 
-class DeletedError(Exception):
-    """camkifu.core.exceptions.DeletedError (exceptions.py:31-45): a move targets a location the user just deleted."""
+class DeletedError(ValueError):
+    """camkifu.core.exceptions.DeletedError (exceptions.py:46-60): a move targets a location the user just deleted."""
 
     def __init__(self, locations, message=None):
+        if message is None:
+            message = "Location has been deleted by user, so it is locked until pixels change significantly."
         super().__init__(message)
         self.locations = locations
         self.message = message
+
+
+class CorrectionWarning(Warning):
+    """camkifu.core.exceptions.CorrectionWarning (exceptions.py:22-43): user corrections the finder did not learn from."""
+
+    def __init__(self, corrections, message=None):
+        text = "{}" if message is None else str(message)
+        text += " [" + ", ".join("(err:{}, exp:{})".format(e, x) for e, x in corrections) + "]"
+        super().__init__(text)
+        self.corrections = corrections
 
 
 def zone_rect(r: int, c: int, g: int = gsize):
@@ -68,7 +80,8 @@ class StonesFinderBase:
             video = getattr(vmanager, "current_video", None)
             is_img = isinstance(video, str) and video.lower().endswith((".png", ".jpg", ".jpeg"))
             self.bg_init_frames = 0 if is_img else 50
-        self.corrections = queue.Queue(10)
+        self.corrections = queue.Queue(10)          # user corrections, filled from the GUI thread (see corrected())
+        self.saved_bg = np.zeros(self.canonical_shape + (3,), dtype=np.float32)
         self.deleted = {}
         self.nb_del_samples = 50
 
@@ -86,8 +99,46 @@ class StonesFinderBase:
     def _learn_bg(self):
         pass   # the B200 plugins keep the MOG2 background model on the device (plugins._DeviceFrames._learn_bg)
 
+    def corrected(self, err_move, exp_move):
+        """StonesFinder.corrected (stonesfinder.py:323-339): the user removed `err_move` and / or added `exp_move`; the
+        finder's own thread digests it in _learn()."""
+        try:
+            self.corrections.put_nowait((err_move, exp_move))
+        except queue.Full:
+            print("Corrections queue full (%s), ignoring %s -> %s" % (self.corrections.maxsize, err_move, exp_move))
+
     def _learn(self):
-        pass
+        """StonesFinder._learn (stonesfinder.py:178-221). A location the user emptied (a deletion, or the source of a
+        relocation) is put under watch: its appearance is averaged over the next `nb_del_samples` calm frames into
+        `saved_bg`, and until the zone looks different again suggestions there are refused (_check_dels). Corrections of
+        another kind (a stone the detection missed) are reported with a CorrectionWarning, as in the reference."""
+        unhandled = []
+        while True:
+            try:
+                err, exp = self.corrections.get_nowait()
+            except queue.Empty:
+                break
+            if exp is None or (err is not None and (err.x, err.y) != (exp.x, exp.y)):
+                self.deleted[(err.y, err.x)] = self.nb_del_samples
+            else:
+                unhandled.append((err, exp))
+        for (r, c), left in self.deleted.items():
+            if not left:
+                continue
+            try:
+                fg = self.get_foreground()
+            except ValueError:
+                fg = None
+            x0, y0, x1, y1 = self.getrect(r, c)
+            # the reference's test reads np.sum(fg[zone] < 0.1 * area): the number of mask values below that threshold
+            if fg is None or np.sum(fg[x0:x1, y0:y1] < 0.1 * (x1 - x0) * (y1 - y0)):
+                self.saved_bg[x0:x1, y0:y1] += self.goban_img[x0:x1, y0:y1] / self.nb_del_samples
+                self.deleted[(r, c)] = left - 1
+        if unhandled:
+            raise CorrectionWarning(unhandled, message="Unhandled corrections")
+
+    def get_foreground(self):
+        raise ValueError("This StonesFinder doesn't seem to be segmenting background. See self.__init__()")
 
     def _show(self, img, name=None, latency=True, thumbnail=True, loc=None, max_frequ=2):
         pass   # display is the GUI's business
@@ -128,8 +179,18 @@ class StonesFinderBase:
         return self.vmanager.controller.get_stones()
 
     def _check_dels(self, r, c):
-        if (r, c) in self.deleted:
+        """StonesFinder._check_dels (stonesfinder.py:223-245): refuse a location under deletion watch until its zone
+        differs from what was sampled after the deletion by 40 grey levels per pixel on average."""
+        if (r, c) not in self.deleted:
+            return
+        if self.deleted[(r, c)] != 0:
             raise DeletedError(((r, c),), "The zone has been marked as deleted too recently.")
+        x0, y0, x1, y1 = self.getrect(r, c)
+        diff = self.saved_bg[x0:x1, y0:y1] - self.goban_img[x0:x1, y0:y1]
+        if np.sum(np.absolute(diff)) / (diff.shape[0] * diff.shape[1]) < 40:
+            raise DeletedError(((r, c),), "The zone has not changed enough since last deletion.")
+        print("previously user-deleted location: {} now unlocked".format((r, c)))
+        del self.deleted[(r, c)]
 
     def suggest(self, color, r, c, doprint=True):
         self._check_dels(r, c)

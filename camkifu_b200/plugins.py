@@ -322,9 +322,6 @@ def build_classes(Base):
             self.heatmap[:] = None
             self._weights_loaded = False
 
-        def _learn(self):
-            pass
-
         def _load_net(self):
             from . import weights
             eng = self._engine()
