@@ -64,6 +64,29 @@ def zone_rect(r: int, c: int, g: int = gsize):
     return 20 * r, 20 * c, (S - 1 if r == g - 1 else 20 * r + 20), (S - 1 if c == g - 1 else 20 * c + 20)
 
 
+class PosGridMirror:
+    """PosGrid (stonesfinder.py:938-1010): pixel position of every intersection of the canonical image, `mtx[i, j] =
+    (x, y)` int16 — the grid of zone centres, (10 + 20 i, 10 + 20 j) for the 380-pixel, 19-line canonical frame."""
+
+    def __init__(self, size, g=gsize):
+        self.size = size
+        self.mtx = np.zeros((g, g, 2), dtype=np.int16)
+        self.adjust_vect = np.zeros(2, dtype=np.float32)
+        self.adjust_contribs = 0
+        first = size / g / 2
+        last = size - first
+        for i in range(g):
+            for j in range(g):
+                self.mtx[i, j, 0] = (first * (g - 1 - i) + last * i) / (g - 1)
+                self.mtx[i, j, 1] = (first * (g - 1 - j) + last * j) / (g - 1)
+
+    def closest_intersection(self, point):
+        """Row and column of the intersection nearest to the (x, y) point of the canonical image."""
+        d = (self.mtx[:, :, 0].astype(np.int64) - point[0]) ** 2 + (self.mtx[:, :, 1].astype(np.int64) - point[1]) ** 2
+        i, j = np.unravel_index(int(np.argmin(d)), d.shape)
+        return int(i), int(j)
+
+
 class StonesFinderBase:
     """Mirror of camkifu.stone.StonesFinder + the bits of camkifu.core.video.VidProcessor finders rely on."""
 
@@ -73,6 +96,7 @@ class StonesFinderBase:
         self.metadata = {}
         self.goban_img = None
         self.canonical_shape = (canonical_size, canonical_size)
+        self._posgrid = PosGridMirror(canonical_size)
         self.mask_cache = None
         self.zone_area = None
         self.intersections = None

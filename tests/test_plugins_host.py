@@ -176,3 +176,24 @@ def test_user_correction_learning_mirrors_reference():
         f.corrected(None, added)                                # a missed stone: reported, not learnt from
         with pytest.raises(warn):
             f._learn()
+
+
+def test_posgrid_mirror_matches_reference(golden):
+    """hostapi.PosGridMirror against PosGrid.mtx recorded from the reference (geometry_g19.npz) and, when the reference is
+    importable, against PosGrid.closest_intersection on random points."""
+    from camkifu_b200 import hostapi
+    g = golden("geometry_g19.npz")
+    pg = hostapi.PosGridMirror(380)
+    assert pg.mtx.dtype == np.int16 and np.array_equal(pg.mtx, g["posgrid"])
+    from oracle import refimport
+    if refimport.available():
+        refimport.load()
+        from camkifu.stone.stonesfinder import PosGrid
+        ref = PosGrid(380)
+        rng = np.random.default_rng(0)
+        for _ in range(200):
+            pt = (int(rng.integers(0, 380)), int(rng.integers(0, 380)))
+            a, b = ref.closest_intersection(pt), pg.closest_intersection(pt)
+            da = (int(ref.mtx[a[0], a[1], 0]) - pt[0]) ** 2 + (int(ref.mtx[a[0], a[1], 1]) - pt[1]) ** 2
+            db = (int(pg.mtx[b[0], b[1], 0]) - pt[0]) ** 2 + (int(pg.mtx[b[0], b[1], 1]) - pt[1]) ** 2
+            assert da == db          # the same distance (ties between equidistant intersections may resolve differently)
