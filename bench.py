@@ -40,7 +40,7 @@ CNN_MAC_PER_PATCH = {"conv1": 36 * 36 * 75 * 32, "conv2": 32 * 32 * 800 * 32, "c
 assert sum(CNN_MAC_PER_PATCH.values()) == 45434080
 # dram__bytes_read.sum + dram__bytes_write.sum of one cnn_tc_front launch (64 frames), from the ncu --set full capture
 # committed under profiles/ (None until a capture exists for the current kernel)
-FRONT_DRAM_TRAFFIC_BYTES = 27891200 + 153144000   # profiles/r1f_kernels_ncu_full_selected.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+FRONT_DRAM_TRAFFIC_BYTES = 28010400 + 151286000   # profiles/r1q_kernels_ncu_full_selected.csv (dram__bytes_read.sum + dram__bytes_write.sum)
 
 
 def measured_peaks():

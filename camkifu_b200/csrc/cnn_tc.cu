@@ -287,18 +287,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
             mbar_wait(b_tfull + 8 * acc, (i / D::NACC) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
-#pragma unroll 2
-            for (int j = half; j < L::N / 8; j += TC_EPI_WARPS / 4) {
-                float v[8];
-                tc_ld8(taddr + 8 * j, v);
-                if (L::CONCAT) {
-                    float u[8];
-                    tc_ld8(taddr + L::N + 8 * j, u);
-                    tc_ld_wait();
+            // all TMEM loads of this warp's column chunks first, one wait, then the arithmetic and the stores: the
+            // accumulator is released as soon as it is in registers
+            constexpr int NJ = L::N / 8 / (TC_EPI_WARPS / 4);     // chunks of 8 channels per warp
+            static_assert(L::N / 8 % (TC_EPI_WARPS / 4) == 0, "column chunks split evenly over the epilogue warps");
+            float vv[NJ][8], uu[L::CONCAT ? NJ : 1][8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] += u[k];
-                } else {
-                    tc_ld_wait();
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = half + jj * (TC_EPI_WARPS / 4);
+                tc_ld8(taddr + 8 * j, vv[jj]);
+                if (L::CONCAT) tc_ld8(taddr + L::N + 8 * j, uu[jj]);
+            }
+            tc_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = half + jj * (TC_EPI_WARPS / 4);
+                float *v = vv[jj];
+                if (L::CONCAT) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] += uu[jj][k];
                 }
                 const float4 b0 = __ldg((const float4 *)args.bias + 2 * j), b1 = __ldg((const float4 *)args.bias + 2 * j + 1);
                 v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f);
@@ -322,9 +332,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
         }
     }
     tc_fence_before();
