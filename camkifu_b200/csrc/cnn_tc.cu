@@ -357,30 +357,40 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float *v
 // Vertical half of the 2x2 max pooling after conv4 (its epilogue already took the horizontal half): hi/lo planes
 // [2][KC][in_plane] on an H x WP grid per patch -> fc1's per-tap planes, tap q = oy * WP + ox:
 //   out[((q * KC + chunk) * out_plane + patch]  (hi),  out[((H/2 * WP + q) * KC + chunk) * out_plane + patch]  (lo)
-// Patch is the fastest index of a thread block so that the writes of fc1's planes are coalesced.
+// The input is patch-major, the output patch-minor: one block stages the (contiguous) units of PB patches of one chunk in
+// shared memory with coalesced 16-byte loads, then writes every tap as a run of PB consecutive patches.
+#define POOL_PB 16
 template <int H, int WP, int KC>
 __global__ void __launch_bounds__(256) cnn_tc_pool_rows(const uint4 *__restrict__ in, long long in_plane, int n_patches,
                                                         uint4 *__restrict__ out, long long out_plane)
 {
-    constexpr int OH = H / 2;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n_patches * OH * WP * KC) return;
-    const int patch = (int)(idx % n_patches);
-    long long t = idx / n_patches;
-    const int c = (int)(t % KC); t /= KC;
-    const int ox = (int)(t % WP), oy = (int)(t / WP);
-    const long long ip = (long long)patch * (H * WP) + (2 * oy) * WP + ox;
-    const uint4 *ph = in + (long long)c * in_plane + ip, *pl = in + (long long)(KC + c) * in_plane + ip;
-    float m[8], v[8];
-    unpack8(__ldg(ph), __ldg(pl), m);
-    unpack8(__ldg(ph + WP), __ldg(pl + WP), v);
+    constexpr int OH = H / 2, UNITS = H * WP, PITCH = UNITS + 1;   // +1: patches fall in different banks
+    __shared__ uint4 s_hi[POOL_PB * PITCH], s_lo[POOL_PB * PITCH];
+    const int c = blockIdx.y, p0 = blockIdx.x * POOL_PB;
+    const int np = min(POOL_PB, n_patches - p0);
+    const uint4 *gh = in + (long long)c * in_plane + (long long)p0 * UNITS;
+    const uint4 *gl = in + (long long)(KC + c) * in_plane + (long long)p0 * UNITS;
+    for (int u = threadIdx.x; u < np * UNITS; u += blockDim.x) {
+        const int p = u / UNITS, r = u - p * UNITS;
+        s_hi[p * PITCH + r] = __ldg(gh + u);
+        s_lo[p * PITCH + r] = __ldg(gl + u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < OH * WP * POOL_PB; t += blockDim.x) {
+        const int p = t % POOL_PB, q = t / POOL_PB;
+        if (p >= np) continue;
+        const int oy = q / WP, ox = q - oy * WP;
+        const int r = (2 * oy) * WP + ox;
+        float m[8], v[8];
+        unpack8(s_hi[p * PITCH + r], s_lo[p * PITCH + r], m);
+        unpack8(s_hi[p * PITCH + r + WP], s_lo[p * PITCH + r + WP], v);
 #pragma unroll
-    for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
-    uint4 hi, lo;
-    split8(m, hi, lo);
-    const int q = oy * WP + ox;
-    out[((long long)q * KC + c) * out_plane + patch] = hi;
-    out[((long long)(OH * WP + q) * KC + c) * out_plane + patch] = lo;
+        for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
+        uint4 hi, lo;
+        split8(m, hi, lo);
+        out[((long long)q * KC + c) * out_plane + p0 + p] = hi;
+        out[((long long)(OH * WP + q) * KC + c) * out_plane + p0 + p] = lo;
+    }
 }
 
 // test aid: planes [2][KC][plane] -> dense float32 [pixel][C]
@@ -596,7 +606,7 @@ static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t
                                   (long long)P * 256, P, st));
     TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
                                   (long long)P * 196, P, st));
-    cnn_tc_pool_rows<12, 6, 12><<<(unsigned)(((long long)P * 36 * 12 + 255) / 256), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
+    cnn_tc_pool_rows<12, 6, 12><<<dim3((unsigned)((P + POOL_PB - 1) / POOL_PB), 12), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
     CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool4");
     TC_TRY(launch_layer<Fc1Cfg>(ctx, "cnn_tc_fc1", p4, W.p4_plane, B.off_w[4], B.off_b[4], nullptr, 0, f5, P, P, st));
     return ckb_launch_fc2_decode(ctx, f5, nf, work + W.tmp, d_softmax, d_stones, d_conf, d_keep, st);
