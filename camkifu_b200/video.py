@@ -108,12 +108,13 @@ class FrameSource:
 
 
 def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int = 32, cnn_params=None, engine=None,
-                  rng_state: int = None, rank: int = None, world: int = None, gather: bool = True):
+                  rng_state: int = None, rank: int = None, world: int = None, gather: bool = True, pipeline=None):
     """Board states of every frame of a video under one board homography `mtx` (a fixed camera: the reference's manual
     board finder). Returns {name: array [n_frames, ...]} — "stones"/"keep"/"conf" (neural), "km_stones"/"km_trusted"
     (clustering: full-board find_stones per frame, RNG state replayed per frame index so that the result does not depend
     on the sharding). With torch.distributed initialised (or rank/world given) each rank processes its frame range and,
-    if `gather`, the states are all-gathered so that every rank returns the whole video."""
+    if `gather`, the states are all-gathered so that every rank returns the whole video. `pipeline`: an existing
+    DetectPipeline to reuse (anything with its detect_stream / eng interface)."""
     import collections
     import torch.distributed as dist
     from .engine import rng_seed, rng_advance
@@ -125,7 +126,7 @@ def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int
     _, n_total, H, W = open_source(source)
     start, stop = sharding.shard_range(n_total, rank, world)
     src = FrameSource(source, start, stop, batch=batch, depth=5)
-    pipe = DetectPipeline(H, W, gsize, mode=mode, sub_batch=min(16, batch), cnn_params=cnn_params, engine=engine)
+    pipe = pipeline or DetectPipeline(H, W, gsize, mode=mode, sub_batch=min(16, batch), cnn_params=cnn_params, engine=engine)
     st0 = rng_seed(0) if rng_state is None else rng_state
     inflight = collections.deque()
 
@@ -149,7 +150,7 @@ def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int
             shape = (0,) if k == "km_trusted" else (0, gsize, gsize)
             out[k] = np.zeros(shape, np.float32 if k == "conf" else np.uint8)
     if gather and world > 1:
-        dev = pipe.eng.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        dev = pipe.eng.device if dist.get_backend() == "nccl" else torch.device("cpu")   # gloo gathers on the host
         for k in names:
             out[k] = sharding.gather_board_states(torch.from_numpy(out[k]).to(dev), n_total).cpu().numpy()
     return out

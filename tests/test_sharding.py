@@ -63,3 +63,45 @@ def test_gather_board_states_gloo_world2(n):
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+class _FakePipeline:
+    """Stands in for DetectPipeline on a host without a GPU: a deterministic function of each frame, so that the ingest,
+    sharding and gather logic of process_video can run under gloo."""
+
+    class eng:
+        device = torch.device("cpu")
+
+    def detect_stream(self, batches, depth=2):
+        for frames, mtx, st in batches:
+            f = frames.numpy().astype(np.int64)
+            s = (f.reshape(f.shape[0], -1).sum(1)[:, None, None] + np.arange(361).reshape(19, 19)[None]) % 3
+            yield {"stones": s.astype(np.uint8), "keep": (s > 0).astype(np.uint8),
+                   "conf": (s / 2.0).astype(np.float32)}
+
+
+def _video_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from camkifu_b200.video import process_video
+        frames = np.random.default_rng(0).integers(0, 256, (29, 24, 32, 3), dtype=np.uint8)
+        res = process_video(frames, np.eye(3), mode="neural", batch=4, pipeline=_FakePipeline())
+        ref = next(_FakePipeline().detect_stream([(torch.from_numpy(frames), None, 0)]))
+        out[rank] = all(np.array_equal(res[k], ref[k]) for k in ref) and res["stones"].shape == (29, 19, 19)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_process_video_shards_and_gathers_gloo_world2():
+    """process_video under torch.distributed (gloo, 2 ranks, CPU): each rank decodes and processes its own frame range
+    (starts aligned to 3) and both end up with the whole video's board states in frame order."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_video_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
