@@ -287,7 +287,8 @@ def run_b200(args, rank, world, local_rank):
                     "sample": "%d frames of the same clip: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "
                               "for Keras predict, one 100-patch batch per frame) + decode" % cpu_n}
     else:
-        cpu_line = None      # timed at N = 1 (see the N = 1 line / --impl reference)
+        cpu_line = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "not timed at N > 1: see the N = 1 line and --impl reference"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
