@@ -148,6 +148,9 @@ struct __align__(16) KmShared {
     } u;
     int csum[9][KM_MAX_CHUNK];             // uint8 input: exact integer member sums per chunk         (Lloyd)
     int ch0;                               // first chunk whose float32 running sums must be taken serially
+    int seg_a[9][KM_CH / 32];              // uint8 input, sums in [2^24, 2^25): per 32-pixel segment sum of (x >> 1) ...
+    int seg_f[9][KM_CH / 32];              // ... and the segment's rounding automaton (see the Lloyd loop)
+    int mode_serial, mode_slow;
     double red_d[KM_MAX_WARPS * 3];
     int red_i[KM_MAX_WARPS * 4];
     float cen[9];
@@ -482,41 +485,136 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
             xn[q] = vn[q] ? load_px<F32>(px, i) : make_float3(0.f, 0.f, 0.f);
         }
         for (int ch = ch0; ch < nchunk; ch++) {
+            int labq[Q];
+            float3 xc[Q];
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 const int p = q * NT + tid;
-                if (p >= KM_CH) continue;
-                const float3 x = xn[q];
-                const int lab = vn[q] ? argmin3(x, oc) : -1;
-                if (F32) {          // uint8 input counted its members in pass 1
-                    c0n += lab == 0;
-                    c1n += lab == 1;
-                    c2n += lab == 2;
-                }
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const bool m = lab == k;
-                    sh.u.planes[3 * k + 0][p] = m ? x.x : 0.f;
-                    sh.u.planes[3 * k + 1][p] = m ? x.y : 0.f;
-                    sh.u.planes[3 * k + 2][p] = m ? x.z : 0.f;
-                }
-                const int i = (ch + 1) * KM_CH + p;  // prefetch the next chunk while warp 0 runs the serial sums
-                vn[q] = i < N;
+                xc[q] = xn[q];
+                labq[q] = (p < KM_CH && vn[q]) ? argmin3(xc[q], oc) : -1;
+                const int i = (ch + 1) * KM_CH + p;      // fetch the next chunk's pixels while this one is summed
+                vn[q] = p < KM_CH && i < N;
                 xn[q] = vn[q] ? load_px<F32>(px, i) : make_float3(0.f, 0.f, 0.f);
             }
-            __syncthreads();
-            if (warp == 0 && lane < 9) {
-                const float4 *pl = (const float4 *)sh.u.planes[lane];
-#pragma unroll 8
-                for (int p = 0; p < KM_CH / 4; p++) {
-                    const float4 v = pl[p];
-                    acc = __fadd_rn(acc, v.x);
-                    acc = __fadd_rn(acc, v.y);
-                    acc = __fadd_rn(acc, v.z);
-                    acc = __fadd_rn(acc, v.w);
+            // uint8 input: decide how this chunk's sums are taken. A running sum that stays <= 2^24 is exact (add the
+            // chunk's integer sum); one in [2^24, 2^25) is an even integer 2u and float32 addition of an integer x
+            // acts on u as  u += (x >> 1) + (x odd ? (u + (x >> 1)) & 1 : 0)  (ties go to the even significand), a
+            // two-state automaton on the parity of u that is evaluated in parallel below; only the chunk in which a
+            // sum crosses 2^24, or one that could reach 2^25, is walked serially.
+            bool serial = true;
+            unsigned slow = 0u;
+            if (!F32) {
+                if (warp == 0) {
+                    int need = 0, sl = 0;
+                    if (lane < 9) {
+                        const int cur = (int)acc;                       // exact: acc is an integer below 2^25
+                        if (cur < (1 << 24)) need = cur + sh.csum[lane][ch] > (1 << 24);
+                        else { sl = 1; need = cur + KM_CH * 255 >= (1 << 25); }
+                    }
+                    const unsigned nb = __ballot_sync(0xffffffffu, need), sb = __ballot_sync(0xffffffffu, sl);
+                    if (lane == 0) { sh.mode_serial = nb != 0u; sh.mode_slow = (int)(sb & 0x1ffu); }
                 }
+                __syncthreads();
+                serial = sh.mode_serial != 0;
+                slow = (unsigned)sh.mode_slow;
             }
-            __syncthreads();
+            if (serial) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const int p = q * NT + tid;
+                    if (p >= KM_CH) continue;
+                    const float3 x = xc[q];
+                    const int lab = labq[q];
+                    if (F32) {          // uint8 input counted its members in pass 1
+                        c0n += lab == 0;
+                        c1n += lab == 1;
+                        c2n += lab == 2;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const bool m = lab == k;
+                        sh.u.planes[3 * k + 0][p] = m ? x.x : 0.f;
+                        sh.u.planes[3 * k + 1][p] = m ? x.y : 0.f;
+                        sh.u.planes[3 * k + 2][p] = m ? x.z : 0.f;
+                    }
+                }
+                __syncthreads();
+                if (warp == 0 && lane < 9) {
+                    const float4 *pl = (const float4 *)sh.u.planes[lane];
+#pragma unroll 8
+                    for (int p = 0; p < KM_CH / 4; p++) {
+                        const float4 v = pl[p];
+                        acc = __fadd_rn(acc, v.x);
+                        acc = __fadd_rn(acc, v.y);
+                        acc = __fadd_rn(acc, v.z);
+                        acc = __fadd_rn(acc, v.w);
+                    }
+                }
+                __syncthreads();
+            } else {
+                // per 32-pixel segment (= one warp's pixels, in pixel order) and slow chain: A = sum of x >> 1 over the
+                // members, and the segment's automaton: has_odd, the parity the segment leaves behind (c), the term
+                // q of its first odd member (whose increment is p_in ^ q), and the increments D of its other odd
+                // members, each of which sees parity 0 after the previous odd member plus the even members in between
+                for (unsigned rest = slow; rest; rest &= rest - 1) {
+                    const int c = __ffs(rest) - 1, k = c / 3, j = c - 3 * k;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        const int p = q * NT + tid;
+                        if (p >= KM_CH) continue;               // warp-uniform: NT and KM_CH are multiples of 32
+                        const bool mem = labq[q] == k;
+                        const int xi = (int)(j == 0 ? xc[q].x : (j == 1 ? xc[q].y : xc[q].z));
+                        const int a = mem ? (xi >> 1) : 0;
+                        const bool odd = mem && (xi & 1), cb = mem && !(xi & 1) && (a & 1);
+                        const unsigned mo = __ballot_sync(0xffffffffu, odd), mc = __ballot_sync(0xffffffffu, cb);
+                        const unsigned below = (1u << lane) - 1u, ob = mo & below;
+                        int dl = 0, qf = 0;
+                        if (odd) {
+                            if (ob) {
+                                const int last = 31 - __clz(ob);
+                                dl = (__popc(mc & below & ~((2u << last) - 1u)) ^ a) & 1;
+                            } else {
+                                qf = (__popc(mc & below) ^ a) & 1;
+                            }
+                        }
+                        const int A = __reduce_add_sync(0xffffffffu, a);
+                        const int D = __popc(__ballot_sync(0xffffffffu, dl != 0));
+                        const int qfirst = __ballot_sync(0xffffffffu, qf != 0) != 0u;
+                        int cw;
+                        if (mo) {
+                            const int top = 31 - __clz(mo);
+                            cw = top == 31 ? 0 : (__popc(mc >> (top + 1)) & 1);
+                        } else {
+                            cw = __popc(mc) & 1;
+                        }
+                        if (lane == 0) {
+                            sh.seg_a[c][p >> 5] = A;
+                            sh.seg_f[c][p >> 5] = (mo != 0u) | (cw << 1) | (qfirst << 2) | (D << 3);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (warp == 0 && lane < 9) {
+                    const int cur = (int)acc;
+                    if (!((slow >> lane) & 1u)) {
+                        acc = (float)(cur + sh.csum[lane][ch]);        // exact regime
+                    } else {
+                        int u = cur >> 1, par = u & 1, add = 0;
+                        for (int sg = 0; sg < KM_CH / 32; sg++) {
+                            const int f = sh.seg_f[lane][sg];
+                            add += sh.seg_a[lane][sg];
+                            if (f & 1) {
+                                add += (f >> 3) + (par ^ ((f >> 2) & 1));
+                                par = (f >> 1) & 1;
+                            } else {
+                                par ^= (f >> 1) & 1;
+                            }
+                        }
+                        acc = (float)((u + add) << 1);                 // even and below 2^25: exact
+                    }
+                }
+                __syncthreads();
+            }
         }
         KM_TICK(3);   // serial chunks
         if (warp == 0 && lane < 9) sh.sums[lane] = acc;

@@ -107,6 +107,27 @@ def test_noise_and_degenerate_images(engine, oracle):
         compare(res, k, ref)
 
 
+def test_float32_sums_past_2_24(engine, oracle):
+    """uint8 images whose cluster sums leave the range where float32 holds integers exactly. OpenCV adds the members one
+    by one in float32; the kernel takes exact integer sums up to 2^24, evaluates the rounding of sums in [2^24, 2^25)
+    as a parity automaton in parallel, and walks serially only across 2^24 and towards 2^25. Bright images put most of
+    the board into one cluster: (0) sums cross 2^24 a third of the way in, (1) they get within reach of 2^25, (2) nearly
+    all pixels are 255: beyond 2^25. Centres, labels and compactness must still be OpenCV's bits."""
+    rng = np.random.default_rng(21)
+    imgs = np.zeros((3, 380, 380, 3), np.uint8)
+    for k, (frac, lo) in enumerate(((0.62, 180), (0.86, 215), (0.985, 255))):
+        bright = rng.random((380, 380)) < frac
+        imgs[k] = np.where(bright[:, :, None], rng.integers(lo, 256, (380, 380, 3)),
+                           np.where(rng.random((380, 380, 1)) < 0.5, rng.integers(0, 40, (380, 380, 3)),
+                                    rng.integers(90, 130, (380, 380, 3)))).astype(np.uint8)
+    states = [engine.L.ckb_rng_seed(300 + k) for k in range(3)]
+    res = engine.find_stones(torch.from_numpy(imgs).cuda(), states, want=ALL)
+    for k in range(3):
+        ref = oracle.c_find_stones(imgs[k], states[k])
+        compare(res, k, ref)
+    assert res["centers"][0].max() > 200
+
+
 @pytest.mark.parametrize("gsize", [9, 13])
 def test_other_board_sizes(oracle, gsize):
     from camkifu_b200.engine import StoneEngine
