@@ -18,7 +18,8 @@
 // with one dependent FADD per pixel each (adding +0 for non-members is exact). The dependent-add latency (4 cycles)
 // bounds such an iteration at ~0.3 ms for a whole board. For uint8 images (the canonical image itself, as opposed
 // to SfClustering's float32 running average) the sums are integers that float32 represents exactly below 2^24, so
-// the serial walk is only needed from the chunk where a running sum first passes 2^24 — see the Lloyd loop.
+// the serial walk is only needed in the chunk where a running sum passes 2^24 (beyond it, up to 2^25, the rounding
+// is a two-state parity automaton that is evaluated in parallel) — see the Lloyd loop.
 // Throughput comes from running many (frame, attempt) CTAs side by side: grid = 3 attempts x n frames, 256 threads.
 //
 // Kernels:  ckb_pack_region_*   region pixels -> linear, vector-loadable scratch (uchar4 / float4 per pixel)
