@@ -143,3 +143,26 @@ def test_other_board_sizes(oracle, gsize):
     ref = oracle.c_find_stones(goban[0].cpu().numpy(), st, gsize)
     compare(res, 0, ref)
     assert np.array_equal(ref["stones"], stones)
+
+
+def test_random_subregions_vs_oracle(engine, oracle):
+    """SfMeta calls find_stones on sub-regions of 6-7 rows / columns (sf_meta.py:253): random regions, uint8 and float32
+    images, against the oracle (labels, centres, ratios, stones, density verdict)."""
+    rng = np.random.default_rng(33)
+    frames, M, truth, _ = synth.make_clip(17, 2, 360, 480)
+    import cv2
+    gob = np.stack([cv2.warpPerspective(f, M, (380, 380)) for f in frames])
+    f32 = (gob[0].astype(np.float32) * 0.8 + gob[1].astype(np.float32) * 0.2)
+    for t in range(8):
+        rs, cs = int(rng.integers(0, 13)), int(rng.integers(0, 13))
+        re, ce = rs + int(rng.integers(4, 8)), cs + int(rng.integers(4, 8))
+        re, ce = min(re, 19), min(ce, 19)
+        st = engine.L.ckb_rng_seed(500 + t)
+        if t % 2:
+            img = torch.from_numpy(f32).cuda()[None]
+            ref = oracle.c_find_stones(f32, st, 19, rs, re, cs, ce)
+        else:
+            img = torch.from_numpy(gob[t % 2:t % 2 + 1]).cuda()
+            ref = oracle.c_find_stones(gob[t % 2], st, 19, rs, re, cs, ce)
+        res = engine.find_stones(img, [st], rs, re, cs, ce, want=ALL)
+        compare(res, 0, ref)
