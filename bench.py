@@ -4,17 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[1] — SfNeural CNN stone classification on synthetic 1080p 19x19 frames,
-64 frames per step on each GPU: ckb_warp (cv2.warpPerspective, stonesfinder.py:140) -> ckb_cnn_forward
+Headline workload (config.workload): BASELINE.json configs[1] — SfNeural CNN stone classification on synthetic 1080p 19x19
+frames, 64 frames per step on each GPU: ckb_warp (cv2.warpPerspective, stonesfinder.py:140) -> ckb_cnn_forward
 (NNCache.predict_all_stones + the 0.6 confidence rule, nn_cache.py:25-52, sf_neural.py:57-70). Random-init (Glorot) weights
 of the reference architecture: the trained weights do not ship with the reference.
 
-`value`   frames/s with the frames resident in HBM, CUDA events on the launching stream, max over ranks.
-`e2e`     the same metric through camkifu_b200.pipeline.DetectPipeline.detect_stream() with HOST (pinned) frames: H2D of
-          the frames and D2H of the board states inside the timed region (batch k+1 uploads while batch k computes).
-`roofline` dominant kernel = cnn_tc_front (patch gather + conv1 + conv2 + pool on tcgen05); achieved = algorithmic FLOP / mean launch time measured with
-          CUDA events in the timed region (ckb_profile_begin/end); peak from MEASURED_PEAKS.json.
-`cpu_baseline` the reference's CPU path (cv2 warp + fp32 CNN, oracle/) on a bounded sample, timed on this host.
+`value`     frames/s of that step with the frames resident in HBM, CUDA events on the launching stream, max over ranks.
+`value_sustained`  the same step back to back for >= 2 s (the offline-video workload is sustained by nature).
+`e2e`       the same metric through camkifu_b200.pipeline.DetectPipeline.detect_stream() with HOST (pinned) frames: H2D of
+            the frames and D2H of the board states inside the timed region (batch k+1 uploads while batch k computes).
+`pipeline`  BASELINE.json configs[2], the whole north-star path on the same 64 x 1080p batches: warp -> MOG2 background
+            model + per-zone foreground counts -> running average -> full-board k-means + zone vote -> CNN predict_all;
+            resident (`value`, `value_sustained`), end to end (`e2e`, DetectPipeline(mode="full")) and on the CPU.
+`roofline`  the dominant kernel (cnn_tc_front: patch gather + conv1 + conv2 + pool on tcgen05) and, under "kernels", the
+            byte-bound kernels of the pipeline against the measured HBM peak: achieved = algorithmic bytes or FLOP per
+            launch / mean launch time measured with CUDA events inside the
+            timed region (ckb_profile_begin/end); peaks from MEASURED_PEAKS.json.
+`cpu_baseline`  the reference's CPU path (cv2 warp + fp32 CNN, oracle/) on bounded samples, timed on this host, with the
+            variants BASELINE.md section 3 lists (threads, MOG2 on, the reference's 100 x batch-1 predict pattern).
 `--impl reference` times that CPU path alone with all host threads and prints the same line with "impl": "reference".
 """
 import argparse
@@ -33,28 +40,42 @@ import numpy as np  # noqa: E402
 
 METRIC = "stone-detect frames/s @1080p 19x19"
 UNIT = "frames/s"
-H, W, GSIZE, BATCH = 1080, 1920, 19, 64
+H, W, GSIZE, BATCH, S = 1080, 1920, 19, 64, 380
 WORKLOAD = "SfNeural CNN stone classification, synthetic 1080p 19x19 frames, 64 frames per step per GPU (warp + CNN + decode)"
+PIPE_WORKLOAD = ("full warp + MOG2 + running average + full-board k-means + zone vote + CNN pipeline, synthetic 1080p "
+                 "19x19 frames, 64 frames per step per GPU (BASELINE.json configs[2])")
 CNN_MAC_PER_PATCH = {"conv1": 36 * 36 * 75 * 32, "conv2": 32 * 32 * 800 * 32, "conv3": 14 * 14 * 288 * 90,
                      "conv4": 12 * 12 * 810 * 90, "fc1": 3240 * 160, "fc2": 160 * 81}
 assert sum(CNN_MAC_PER_PATCH.values()) == 45434080
-# dram__bytes_read.sum + dram__bytes_write.sum of one cnn_tc_front launch (64 frames), from the ncu --set full capture
-# committed under profiles/ (None until a capture exists for the current kernel)
-FRONT_DRAM_TRAFFIC_BYTES = 28010400 + 151286000   # profiles/r1q_kernels_ncu_full_selected.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+N_FULL = 379 * 379
+KMEANS_BYTES_PER_FRAME = 3 * N_FULL + 4 * N_FULL + 1083          # region read once + labels + ratios
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (64 frames) from the `ncu --set full` captures under profiles/
+# (None = no capture of the current kernel yet)
+DRAM_TRAFFIC = {
+    "cnn_tc_front": 28010400 + 151286000,      # profiles/r1q_kernels_ncu_full_selected.csv
+    "ckb_warp_kernel": None,
+    "ckb_kmeans_cluster": None,
+    "ckb_mog2_kernel": None,
+}
+SOFTMAX_TOLERANCE = ("CNN softmax vs the fp32 oracle: max_j |y_j - y_ref_j| / max_j y_ref_j <= 1e-3 per patch "
+                     "(scale-relative, tests/test_gpu_cnn.py) with identical argmax; warp, k-means labels / centres, "
+                     "MOG2 masks, board states: bit-exact")
 
 
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
-                "source": "MEASURED_PEAKS.json (sustained bf16)"}
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "MEASURED_PEAKS.json"}
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clocks and throttle reasons through NVML while a timed region runs."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -100,32 +121,85 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_fps(frames, mtx, params, threads: int, budget_s: float = 15.0, max_frames: int = 64):
-    """The reference's per-frame CPU path on this host: cv2.warpPerspective (stonesfinder.py:140) + the SfNeural net on
-    the 100 patches + decode (nn_cache.py:25-52). Keras/Theano are not installed anywhere here, so `net.predict` is the
-    oracle's fp32 torch-CPU stand-in, fed one 100-patch batch per frame (kinder than the reference's 100 batch-1 calls).
-    Returns (frames/s, frames timed)."""
+class CpuPath:
+    """The reference's per-frame CPU path on this host, restated with the third-party calls it makes (oracle.RefPath):
+    cv2.warpPerspective (stonesfinder.py:140), cv2 MOG2 (stonesfinder.py:171-176), SfClustering's running average and
+    find_stones (sf_clustering.py:33-36,48-178: cv2.kmeans + the 361-zone np.unique loop) and the SfNeural net on the
+    100 patches + decode (nn_cache.py:25-52). Keras / Theano are not installed anywhere here, so `net.predict` is the
+    oracle's fp32 torch-CPU stand-in."""
+
+    def __init__(self, params, threads: int):
+        import cv2
+        import torch
+        from oracle import oracle as O
+        self.cv2, self.O, self.threads = cv2, O, threads
+        cv2.setNumThreads(threads)
+        torch.set_num_threads(threads)
+        self.predict = O.torch_cnn(params)
+        self.ref = O.RefPath(GSIZE)
+        self.bg = cv2.createBackgroundSubtractorMOG2(detectShadows=False)
+        self.seen = 0
+
+    def neural(self, frame, mtx, mog2=False, batch1=False):
+        g = self.cv2.warpPerspective(frame, mtx, (S, S))
+        if mog2:
+            self.bg.apply(g, learningRate=0.01 if self.seen < 50 else 0.005)
+            self.seen += 1
+        x = self.O.c_nn_gather(g)
+        if batch1:      # the reference's own pattern: one predict call per region (nn_cache.py:50)
+            y = np.concatenate([self.predict(x[i:i + 1]) for i in range(100)])
+        else:           # kinder to the reference: one 100-patch batch per frame
+            y = self.predict(x)
+        return self.O.c_nn_decode(y)
+
+    def full(self, frame, mtx):
+        g = self.cv2.warpPerspective(frame, mtx, (S, S))
+        self.bg.apply(g, learningRate=0.01 if self.seen < 50 else 0.005)
+        self.seen += 1
+        self.ref.accumulate(g)
+        self.ref.find_stones(g)
+        return self.O.c_nn_decode(self.predict(self.O.c_nn_gather(g)))
+
+    def fps(self, fn, frames, n_frames, reps, **kw):
+        """median frames/s over `reps` repetitions of `n_frames` frames (one untimed frame first)."""
+        fn(frames[0], self.mtx, **kw)
+        vals = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for k in range(n_frames):
+                fn(frames[k % len(frames)], self.mtx, **kw)
+            vals.append(n_frames / (time.perf_counter() - t0))
+        return statistics.median(vals)
+
+
+def cpu_baseline_block(frames, mtx, params):
+    threads = os.cpu_count() or 1
+    cp = CpuPath(params, threads)
+    cp.mtx = mtx
+    main = cp.fps(cp.neural, frames, 64, 5)
+    variants = {
+        "neural_mog2_on": {"value": cp.fps(cp.neural, frames, 64, 5, mog2=True), "threads": threads,
+                           "sample": "64 frames x 5, median; + cv2 MOG2 apply per frame as the reference always runs it"},
+        "neural_batch1_predict": {"value": cp.fps(cp.neural, frames, 8, 3, mog2=True, batch1=True), "threads": threads,
+                                  "sample": "8 frames x 3, median; MOG2 on and the reference's 100 batch-1 predict calls per frame"},
+        "pipeline_full": {"value": cp.fps(cp.full, frames, 16, 3), "threads": threads,
+                          "sample": "16 frames x 3, median; warp + MOG2 + running average + cv2.kmeans full board + "
+                                    "361-zone np.unique loop + CNN (config 3)"},
+    }
+    cp1 = CpuPath(params, 1)
+    cp1.mtx = mtx
+    variants["neural_1_thread"] = {"value": cp1.fps(cp1.neural, frames, 16, 5), "threads": 1,
+                                   "sample": "16 frames x 5, median; cv2 / torch limited to one thread"}
     import cv2
     import torch
-    from oracle import oracle as O
     cv2.setNumThreads(threads)
     torch.set_num_threads(threads)
-    predict = O.torch_cnn(params)
-    done, t0 = 0, time.perf_counter()
-    # one untimed frame (thread pools, allocator)
-    g = cv2.warpPerspective(frames[0], mtx, (380, 380))
-    predict(O.c_nn_gather(g))
-    t0 = time.perf_counter()
-    while done < max_frames:
-        f = frames[done % len(frames)]
-        g = cv2.warpPerspective(f, mtx, (380, 380))
-        y = predict(O.c_nn_gather(g))
-        O.c_nn_decode(y)
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return done / dt, done
+    for v in variants.values():
+        v["unit"] = UNIT
+    return {"value": main, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "64 frames of the same clip x 5 repetitions, median: cv2.warpPerspective + fp32 CNN (torch-CPU "
+                      "stand-in for Keras predict, one 100-patch batch per frame) + decode; single Python process",
+            "variants": variants}
 
 
 def run_reference(args, rank, world):
@@ -135,12 +209,17 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     frames, mtx, truth, _ = synth.make_clip_parallel(1000, 8, H, W)
     params = weights.glorot_params(seed=0)
-    per_step = max(4, min(16, BATCH))
+    cp = CpuPath(params, threads)
+    cp.mtx = mtx
+    per_step = 32
+    cp.neural(frames[0], mtx)
     times = []
     for s in range(args.warmup + args.steps):
-        fps, n = cpu_reference_fps(frames, mtx, params, threads, budget_s=8.0, max_frames=per_step)
+        t0 = time.perf_counter()
+        for k in range(per_step):
+            cp.neural(frames[k % len(frames)], mtx)
         if s >= args.warmup:
-            times.append(n / fps)
+            times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     value = per_step / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -150,24 +229,53 @@ def run_reference(args, rank, world):
                        "note": "bounded sample of the workload: %d frames per step on the host CPU" % per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d frames/step x %d steps: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "
-                                       "for Keras predict, one 100-patch batch per frame) + decode" % (per_step, args.steps)},
+                                       "for Keras predict, one 100-patch batch per frame) + decode" % (per_step, args.steps),
+                             "median_step_fps": per_step / statistics.median(times)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------------- B200 path
-def run_b200(args, rank, world, local_rank):
+def quad_area(mtx):
+    inv = np.linalg.inv(mtx)
+    pts = []
+    for x, y in ((0, 0), (S, 0), (S, S), (0, S)):
+        v = inv @ np.array([x, y, 1.0])
+        pts.append((v[0] / v[2], v[1] / v[2]))
+    a = 0.0
+    for i in range(4):
+        a += pts[i][0] * pts[(i + 1) % 4][1] - pts[(i + 1) % 4][0] * pts[i][1]
+    return abs(a) / 2
+
+
+def aggregate(prof):
+    agg = {}
+    for name, ms in prof:
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += ms
+        a[1] += 1
+    return agg
+
+
+def kernel_rows(agg, steps):
+    ksum = sum(v[0] for v in agg.values()) or 1.0
+    rows = sorted(((n, v[0] / v[1], v[1]) for n, v in agg.items()), key=lambda x: -x[1] * x[2])
+    return [{"name": n, "ms": round(ms, 4), "launches_per_step": c / steps, "share": round(ms * c / ksum, 4)}
+            for n, ms, c in rows]
+
+
+def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     import torch
     import torch.distributed as dist
     from camkifu_b200 import synth, weights
-    from camkifu_b200.engine import StoneEngine
+    from camkifu_b200.engine import StoneEngine, rng_seed, rng_states
     from camkifu_b200.pipeline import DetectPipeline, pinned_frames
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(gpu_index)
+    dev = torch.device("cuda", gpu_index)
     from camkifu_b200.affinity import bind_to_gpu
-    numa_bound = bind_to_gpu(local_rank) if world > 1 else False   # pinned staging buffers on the GPU's own NUMA node
+    numa_bound = bind_to_gpu(gpu_index) if world > 1 else False   # pinned staging buffers on the GPU's own NUMA node
     eng = StoneEngine(GSIZE, device=dev)
     params = weights.glorot_params(seed=0)
     eng.set_cnn_weights(params)
@@ -179,133 +287,264 @@ def run_b200(args, rank, world, local_rank):
     n_rot = 2   # two resident batches (796 MB > the 126 MB L2): consecutive steps never read the same frames
     resident = [host.to(dev, non_blocking=True)]
     resident.append(torch.roll(resident[0], shifts=7, dims=0).contiguous())
-    goban = torch.empty((BATCH, 380, 380, 3), dtype=torch.uint8, device=dev)
+    goban = torch.empty((BATCH, S, S, 3), dtype=torch.uint8, device=dev)
+    fg = torch.empty((BATCH, S, S), dtype=torch.uint8, device=dev)
+    accu = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+    bg = eng.mog2_new_state()
+    st0 = rng_seed(0)
+    km_states = rng_states(st0, 0, BATCH)
+    km_states_dev = torch.as_tensor(np.asarray(km_states, dtype=np.uint64).astype(np.int64), device=dev)
+    full_state = {"frames": 0}
     torch.cuda.synchronize()
 
-    def step(i):
+    def step_neural(i):
         eng.warp(resident[i % n_rot], mtx, out=goban)
         return eng.cnn_forward(goban, want_softmax=False)
+
+    def step_full(i):
+        f0 = full_state["frames"]
+        eng.warp(resident[i % n_rot], mtx, out=goban)
+        eng.mog2_apply(goban, bg, f0, 0.01 if f0 + BATCH <= 50 else [0.01 if f0 + k < 50 else 0.005 for k in range(BATCH)],
+                       out=fg)
+        cnt = eng.zone_fg_counts(fg)
+        eng.accumulate(goban, accu, first=(f0 == 0))
+        km = eng.find_stones(goban, km_states_dev)
+        nn = eng.cnn_forward(goban, want_softmax=False)
+        full_state["frames"] = f0 + BATCH
+        return nn, km, cnt
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # parity spot check outside the timed region (rank 0): warp bit-exact, board state of frame 0 against the oracle
+    # ---- parity spot check outside the timed regions (rank 0): four frames of the batch against the oracle
     check = None
     if rank == 0:
         from oracle import oracle as O
-        out = step(0)
+        nn, km, cnt = step_full(0)
         torch.cuda.synchronize()
-        g0 = goban[0].cpu().numpy()
-        warp_ok = bool(np.array_equal(g0, O.c_warp(frames_np[0], mtx, 380)))
-        y = O.c_cnn_forward(O.c_nn_gather(g0), params)
-        s_ref, c_ref, k_ref = O.c_nn_decode(y)
-        check = {"warp_bit_exact": warp_ok, "stones_equal": bool(np.array_equal(out["stones"][0].cpu().numpy(), s_ref)),
-                 "conf_max_abs_err": float(np.abs(out["conf"][0].cpu().numpy() - c_ref).max())}
+        full_state["frames"] = 0
+        eng.L.ckb_mog2_reset(eng._h, eng._ptr(bg), eng._stream())
+        g_all = goban.cpu().numpy()
+        nn_st, km_st, km_tr = nn["stones"].cpu().numpy(), km["stones"].cpu().numpy(), km["trusted"].cpu().numpy()
+        predict = O.torch_cnn(params)
+        ok = {"warp_bit_exact": True, "cnn_stones_equal": True, "kmeans_stones_equal": True, "kmeans_vs_truth": True}
+        for k in (0, 21, 42, 63):
+            ok["warp_bit_exact"] &= bool(np.array_equal(g_all[k], O.c_warp(frames_np[k], mtx, S)))
+            s_ref, c_ref, _ = O.c_nn_decode(predict(O.c_nn_gather(g_all[k])))
+            ok["cnn_stones_equal"] &= bool(np.array_equal(nn_st[k], s_ref))
+            ref = O.c_find_stones(g_all[k], km_states[k])
+            ok["kmeans_stones_equal"] &= bool(np.array_equal(km_st[k], ref["stones"]) and bool(km_tr[k]) == ref["trusted"])
+            ok["kmeans_vs_truth"] &= bool(np.array_equal(km_st[k], truth[k]))
+        y = O.c_cnn_forward(O.c_nn_gather(g_all[0]), params)     # the fp32 C oracle on frame 0: confidence error
+        s_ref, c_ref, _ = O.c_nn_decode(y)
+        ok["cnn_stones_equal"] &= bool(np.array_equal(nn_st[0], s_ref))
+        ok["conf_max_abs_err"] = float(np.abs(nn["conf"][0].cpu().numpy() - c_ref).max())
+        ok["frames_checked"] = [0, 21, 42, 63]
+        check = ok
 
-    for i in range(args.warmup):
-        step(i)
+    # the one collective of the path (final gather of per-frame board states): communicator and buffers set up and
+    # warmed outside the timed windows; timed on its own as gather_ms and once inside the `value` window
+    gather_out = gather_ms = None
+    if world > 1:
+        gather_out = torch.empty((world * BATCH, 361), dtype=torch.uint8, device=dev)
+        mine = torch.zeros((BATCH, 361), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            dist.all_gather_into_tensor(gather_out, mine)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(gather_out, mine)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / 5
+
+    def timed_steps(step, steps, warmup, profile=True, gather=False):
+        for i in range(warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(gpu_index)
+        sampler.start()
+        l0 = eng.launches
+        if profile:
+            eng.profile_begin(capacity=max(64, 24 * steps + 32))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for i in range(steps):
+            out = step(warmup + i)
+        if gather and world > 1:
+            o = out[0] if isinstance(out, tuple) else out
+            dist.all_gather_into_tensor(gather_out, o["stones"].reshape(BATCH, 361))
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = eng.profile_end() if profile else []
+        return ms, prof, eng.launches - l0, sampler.finish(), out
+
+    def sustained(step, min_seconds=2.0, chunk=50):
+        """the step back to back for at least `min_seconds` of device time (same on every rank: fixed step count
+        derived from the burst timing would differ per rank, so ranks agree on the count through the chunk loop)"""
+        barrier()
+        sampler = ClockSampler(gpu_index)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n, t0 = 0, time.perf_counter()
+        while True:
+            for i in range(chunk):
+                step(n + i)
+            n += chunk
+            torch.cuda.current_stream().synchronize()
+            flag = torch.tensor([1.0 if time.perf_counter() - t0 < min_seconds else 0.0], device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if float(flag) == 0.0:
+                break
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n, sampler.finish()
+
+    # ---- leg A: headline (config 2), burst over K steps
+    ms_total, prof, launches, clocks, out = timed_steps(step_neural, args.steps, args.warmup, gather=True)
+    # ---- leg B: the same step sustained
+    sus_ms, sus_n, sus_clocks = sustained(step_neural)
+    # ---- leg C / D: the whole pipeline (config 3), burst and sustained
+    pipe_ms, pipe_prof, pipe_launches, pipe_clocks, pipe_out = timed_steps(step_full, args.steps, args.warmup)
+    psus_ms, psus_n, psus_clocks = sustained(step_full)
+
+    # ---- host -> device ceiling of this job: every rank copies a pinned 256 MB buffer at the same time
+    hb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    db = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    db.copy_(hb, non_blocking=True)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = eng.launches
-    eng.profile_begin(capacity=max(64, 16 * args.steps + 16))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = step(args.warmup + i)
-    stones_all = None
-    if world > 1:   # the one collective of the path: final gather of the per-frame board states
-        mine = out["stones"].reshape(BATCH, 361)
-        stones_all = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(stones_all, mine)
-    e1.record()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(8):
+        db.copy_(hb, non_blocking=True)
+    h1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    prof = eng.profile_end()
-    launches = eng.launches - launches0
-    clocks = sampler.finish()
+    h2d_ms = h0.elapsed_time(h1)
+    del hb, db
 
     # ---- end to end: host frames through the public batch API
-    pipe = DetectPipeline(H, W, GSIZE, mode="neural", sub_batch=16, engine=eng)
-    for _ in range(max(1, min(args.warmup, 3))):
-        pipe.detect(host, mtx)
-    barrier()
-    e2e_steps = args.steps
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    # offline-video form of the API: batch k+1 uploads while batch k computes; every result is read back on the host
-    for res in pipe.detect_stream(((host, mtx) for _ in range(e2e_steps)), depth=2):
-        pass
-    f1.record()
-    barrier()
-    e2e_s = f0.elapsed_time(f1) / 1e3
-    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    e2e_ok = bool(np.array_equal(res["stones"], out["stones"].cpu().numpy())) if (args.steps + args.warmup - 1) % n_rot == 0 else None
+    def e2e(mode, sub_batch):
+        pipe = DetectPipeline(H, W, GSIZE, mode=mode, sub_batch=sub_batch, engine=eng)
+        for _ in range(max(1, min(args.warmup, 3))):
+            pipe.detect(host, mtx)
+        barrier()
+        b0 = (pipe.h2d_bytes, pipe.d2h_bytes)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        # offline-video form of the API: batch k+1 uploads while batch k computes; every result is read back on the host
+        res = None
+        for res in pipe.detect_stream(((host, mtx) for _ in range(args.steps)), depth=2):
+            pass
+        f1.record()
+        barrier()
+        return f0.elapsed_time(f1) / 1e3, (pipe.h2d_bytes - b0[0]) // args.steps, (pipe.d2h_bytes - b0[1]) // args.steps, res
+
+    e2e_s, h2d, d2h, res = e2e("neural", 16)
+    e2e_ok = bool(np.array_equal(res["stones"], step_neural(0)["stones"].cpu().numpy()))
+    pe2e_s, ph2d, pd2h, pres = e2e("full", 64)
+    pe2e_ok = bool(np.array_equal(pres["km_stones"], pipe_out[1]["stones"].cpu().numpy()) and
+                   np.array_equal(pres["stones"], pipe_out[0]["stones"].cpu().numpy()))
 
     # ---- max over ranks
-    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms = (float(v) for v in t)
     if rank != 0:
         return
-    ms_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total / 1e3)
-    e2e_value = world * BATCH * e2e_steps / e2e_s
+    fps = lambda steps, ms: world * BATCH * steps / (ms / 1e3)   # noqa: E731
+    value = fps(args.steps, ms_total)
+    h2d_peak = world * 8 * (256 << 20) / (h2d_ms / 1e3) / 1e9
 
-    # ---- per-kernel shares and the roofline of the dominant kernel
-    agg = {}
-    for name, ms in prof:
-        a = agg.setdefault(name, [0.0, 0])
-        a[0] += ms
-        a[1] += 1
-    kern = sorted(((n, v[0] / v[1], v[1]) for n, v in agg.items()), key=lambda x: -x[1] * x[2])
-    ksum = sum(v[0] for v in agg.values())
+    # ---- rooflines
     peaks = measured_peaks()
+    agg, pagg = aggregate(prof), aggregate(pipe_prof)
     front = "cnn_tc_front"          # gather + conv1 + conv2 + pool: the dominant kernel
     front_ms = agg[front][0] / agg[front][1]
     front_flop = 2.0 * (CNN_MAC_PER_PATCH["conv1"] + CNN_MAC_PER_PATCH["conv2"]) * 100 * BATCH
     achieved = front_flop / (front_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": front, "achieved": achieved,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": FRONT_DRAM_TRAFFIC_BYTES, "peak_source": peaks["source"],
+    ksum = sum(v[0] for v in agg.values())
+
+    def hbm_row(names, bytes_per_launch, table, note):
+        ms = sum(table[n][0] / table[n][1] * (table[n][1] / args.steps) for n in names if n in table)
+        if ms <= 0:
+            return None
+        gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+        return {"kernel": "+".join(n for n in names if n in table), "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": DRAM_TRAFFIC.get(names[0]),
+                "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms, "note": note}
+
+    warp_bytes = BATCH * (3 * S * S + 3 * min(4 * S * S, quad_area(mtx)))
+    km_names = ["ckb_kmeans_cluster", "ckb_pack_region", "ckb_kmeans_attempt", "ckb_zone_classify"]
+    mog_bytes = 2 * (25 * 4 + 1) * S * S + BATCH * (3 + 1) * S * S
+    sub = [
+        hbm_row(["ckb_warp_kernel"], warp_bytes, pagg, "3 S^2 written + 3 min(4 S^2, source quad area) read per frame x 64"),
+        hbm_row(km_names, BATCH * KMEANS_BYTES_PER_FRAME, pagg,
+                "compulsory bytes: region pixels read once + int32 labels + ratios per frame x 64; the kernels make ~8 passes "
+                "over pixels held in shared memory (k-means++ 3, Lloyd ~2-3, compactness 1) and are bound by instruction "
+                "issue, not by bytes"),
+        hbm_row(["ckb_mog2_kernel"], mog_bytes, pagg, "model state read + written once per launch + 64 x (image + mask)"),
+    ]
+    roofline = {"bound": "tensor", "kernel": front, "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": DRAM_TRAFFIC[front],
+                "peak_source": peaks["source"] + " (burst bf16: the kernel is timed in a %.0f ms window)" % ms_total,
+                "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
                 "algorithmic_flop_per_launch": front_flop, "ms_per_launch": front_ms,
                 "share_of_step": agg[front][0] / ksum,
                 "note": "algorithmic FLOP = 2 x (3 110 400 conv1 + 26 214 400 conv2) MAC x 6400 patches; the kernel issues 3 "
                         "bf16 products per conv2 MAC and 2 per conv1 MAC (hi/lo operand split for the 1e-3 softmax bar), "
-                        "so ~1/3 is its ceiling in these units"}
+                        "so ~1/3 is its ceiling in these units",
+                "kernels": [r for r in sub if r]}
     cnn_flop = 2.0 * sum(CNN_MAC_PER_PATCH.values()) * 100 * BATCH
     cnn_ms = sum(v[0] for n, v in agg.items() if n.startswith("cnn_")) / args.steps
 
-    # ---- CPU baseline on this host (bounded sample; rank 0 of the N = 1 run only)
+    # ---- CPU baseline on this host (bounded samples; rank 0 of the N = 1 run only)
     threads = os.cpu_count() or 1
     if world == 1:
-        cpu_fps, cpu_n = cpu_reference_fps(frames_np, mtx, params, threads, budget_s=15.0, max_frames=64)
-        cpu_line = {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": "%d frames of the same clip: cv2.warpPerspective + fp32 CNN (torch-CPU stand-in "
-                              "for Keras predict, one 100-patch batch per frame) + decode" % cpu_n}
+        cpu_line = cpu_baseline_block(frames_np, mtx, params)
     else:
         cpu_line = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": "not timed at N > 1: see the N = 1 line and --impl reference"}
 
+    e2e_value = fps(args.steps, e2e_s * 1e3)
+    pe2e_value = fps(args.steps, pe2e_s * 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
-            "data": "synthetic",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frame": [H, W], "gsize": GSIZE, "frames_per_step_per_gpu": BATCH,
                        "weights": "glorot_uniform seed 0 (reference architecture, nn_manager.py:277-298)",
                        "l2": "inputs larger than L2: two resident 398 MB batches used alternately",
                        "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world,
-                       "numa_bound": numa_bound},
+                       "gpu_map": gpu_map, "numa_bound": numa_bound, "tolerance": SOFTMAX_TOLERANCE},
+            "value_sustained": {"value": fps(sus_n, sus_ms), "unit": UNIT, "steps": sus_n, "seconds": sus_ms / 1e3,
+                                "clocks": sus_clocks},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "camkifu_b200.pipeline.DetectPipeline.detect_stream (pinned host frames, ROI upload, 16-frame "
-                           "sub-batches double buffered, results of every batch read back to the host)", "matches_resident_path": e2e_ok},
+                           "sub-batches double buffered, results of every batch read back to the host)",
+                    "matches_resident_path": e2e_ok, "h2d_gbs": world * h2d * args.steps / e2e_s / 1e9,
+                    "h2d_peak_gbs": h2d_peak, "h2d_frac": world * h2d * args.steps / e2e_s / 1e9 / h2d_peak,
+                    "h2d_peak_how": "every rank copying a pinned 256 MB buffer 8 times at once, in this job"},
+            "gather_ms": gather_ms,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_line,
-            "kernels": [{"name": n, "ms": round(ms, 4), "launches_per_step": c / args.steps,
-                         "share": round(ms * c / ksum, 4)} for n, ms, c in kern],
+            "kernels": kernel_rows(agg, args.steps),
             "cnn": {"tflops_algorithmic": cnn_flop / (cnn_ms * 1e-3) / 1e12, "ms_per_step": cnn_ms},
+            "pipeline": {"workload": PIPE_WORKLOAD, "value": fps(args.steps, pipe_ms), "unit": UNIT,
+                         "ms_per_step": pipe_ms / args.steps, "gpu_launches": pipe_launches, "clocks": pipe_clocks,
+                         "value_sustained": {"value": fps(psus_n, psus_ms), "steps": psus_n, "seconds": psus_ms / 1e3,
+                                             "clocks": psus_clocks},
+                         "e2e": {"value": pe2e_value, "unit": UNIT, "h2d_bytes_per_step": ph2d, "d2h_bytes_per_step": pd2h,
+                                 "api": "DetectPipeline(mode='full').detect_stream, 64-frame batches double buffered",
+                                 "matches_resident_path": pe2e_ok, "h2d_gbs": world * ph2d * args.steps / pe2e_s / 1e9},
+                         "kernels": kernel_rows(pagg, args.steps),
+                         "real_time_factor_at_30fps": fps(psus_n, psus_ms) / 30.0},
             "parity_check": check}
     print(json.dumps(line), flush=True)
 
@@ -324,14 +563,18 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # LOCAL_RANK -> physical GPU by PCIe topology: with fewer ranks than GPUs, spread them over distinct host uplinks
+    from camkifu_b200.affinity import pick_gpus
+    gpu_map = pick_gpus(world) if world > 1 else [local_rank]
+    gpu_index = gpu_map[local_rank] if local_rank < len(gpu_map) else local_rank
     if world > 1:
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        torch.cuda.set_device(gpu_index)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", gpu_index))
     try:
-        run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank, gpu_index, gpu_map)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcamkifu_b200.so")
+# CAMKIFU_B200_LIB: an instrumented build of the same library (tools/km_probe.py); never a different implementation
+LIB_PATH = os.environ.get("CAMKIFU_B200_LIB") or os.path.join(HERE, "libcamkifu_b200.so")
 
 CKB_OK = 0
 _lib = None

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcamkifu_b200.so")
-SOURCES = ["ckb_api.cu", "geometry.cu", "warp.cu", "mog2.cu", "kmeans.cu", "cnn_pack.cu", "cnn_simt.cu", "cnn_tc.cu", "cnn_tc_front.cu"]
+SOURCES = ["ckb_api.cu", "geometry.cu", "warp.cu", "mog2.cu", "kmeans.cu", "kmeans_cluster.cu", "cnn_pack.cu", "cnn_simt.cu", "cnn_tc.cu", "cnn_tc_front.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -34,26 +34,28 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None, bdir: str = None) -> str:
+    """extra_flags / out / bdir: instrumented variants for tools/ (e.g. -DKC_TIMING); the product is the default call."""
+    if out is None and not force and up_to_date():
         return OUT
+    out = out or OUT
     objs = []
-    bdir = os.path.join(HERE, "build")
+    bdir = bdir or os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode != 0:
-            print(out)
+            print(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-    subprocess.run([nvcc(), "-shared", "-o", OUT] + objs + ["-lcudart"], check=True)
-    return OUT
+    subprocess.run([nvcc(), "-shared", "-o", out] + objs + ["-lcudart"], check=True)
+    return out
 
 
 if __name__ == "__main__":

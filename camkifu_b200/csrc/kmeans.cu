@@ -26,9 +26,7 @@
 //           ckb_kmeans_attempt  one CTA per (frame, attempt)
 //           ckb_zone_classify   one CTA per frame: best attempt, labels, zone histograms (warp per zone, ballot/popc
 //                               reductions), ratios, stones, density check
-#include <float.h>
-
-#include "ckb_common.cuh"
+#include "kmeans_common.cuh"
 
 #define KM_THREADS_F32 256             // float32 input: the serial centre sums dominate, many small CTAs per SM
 #define KM_MAX_WARPS 32
@@ -38,106 +36,29 @@
 #define KM_CH 512                      // pixels per Lloyd chunk
 #define KM_PLANE (KM_CH + 4)           // +4 words: the nine lanes' 128-bit reads fall in distinct banks
 #define KM_MAX_CHUNK ((KM_MAX_N + KM_CH - 1) / KM_CH)   // 283
-#define KM_MAX_ITER 100                // criteria type has EPS only => maxCount = 100 (the "15" is ignored)
-#define KM_EPS2 9.0                    // (eps = 3)^2
-
-struct KmAttempt {
-    double compactness;
-    float centers[9];      // final centres
-    float old_centers[9];  // the centres the returned labels were assigned against
-    int n_fix;             // empty-cluster repairs of the last iteration (label overrides)
-    int fix_idx[2];
-    int fix_k[2];
-    int iters;
-};
-
-struct Region {
-    int x0, y0, h, w, N;
-};
-
-// ----------------------------------------------------------------------------------------------------------- helpers
-__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz)
-{
-    // hal::normL2Sqr_ for n = 3: ((t0*t0 + t1*t1) + t2*t2) in float32 without contraction
-    const float t0 = __fsub_rn(ax, bx), t1 = __fsub_rn(ay, by), t2 = __fsub_rn(az, bz);
-    float d = __fmul_rn(t0, t0);
-    d = __fadd_rn(d, __fmul_rn(t1, t1));
-    d = __fadd_rn(d, __fmul_rn(t2, t2));
-    return d;
-}
-
-template <bool F32>
-__device__ __forceinline__ float3 load_px(const void *scratch, int i)
-{
-    if (F32) {
-        const float4 v = __ldg((const float4 *)scratch + i);
-        return make_float3(v.x, v.y, v.z);
-    } else {
-        const uchar4 v = __ldg((const uchar4 *)scratch + i);
-        return make_float3((float)v.x, (float)v.y, (float)v.z);
-    }
-}
-
-__device__ __forceinline__ double warp_sum_d(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __forceinline__ double warp_incl_scan_d(double v, int lane)
-{
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
-
-__device__ __forceinline__ uint32_t rng_next(uint64_t &s)
-{
-    s = (uint64_t)(uint32_t)s * 4164903690ULL + (s >> 32);
-    return (uint32_t)s;
-}
-
-__device__ __forceinline__ double rng_double(uint64_t &s)
-{
-    const uint32_t t = rng_next(s);
-    const uint64_t v = ((uint64_t)t << 32) | rng_next(s);
-    return __dmul_rn(__ull2double_rn(v), 5.4210108624275221700372640043497e-20);
-}
-
-// label = first minimum of the three float32 distances (KMeansDistanceComputer: `if (min_dist > dist)`)
-__device__ __forceinline__ int argmin3(float3 x, const float *c)
-{
-    const float d0 = dist3(x.x, x.y, x.z, c[0], c[1], c[2]);
-    const float d1 = dist3(x.x, x.y, x.z, c[3], c[4], c[5]);
-    const float d2 = dist3(x.x, x.y, x.z, c[6], c[7], c[8]);
-    int k = 0;
-    float m = d0;
-    if (m > d1) { m = d1; k = 1; }
-    if (m > d2) { k = 2; }
-    return k;
-}
 
 // ------------------------------------------------------------------------------------------------------------- pack
 template <bool F32>
 __global__ void __launch_bounds__(256) ckb_pack_region(const void *__restrict__ imgs, int S, Region rg,
-                                                       void *__restrict__ scratch, size_t scratch_stride)
+                                                       void *__restrict__ scratch, size_t scratch_stride,
+                                                       const KmAttempt *__restrict__ only_flagged)
 {
     const int f = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rg.N) return;
-    const int row = i / rg.w, col = i - row * rg.w;
-    const size_t src = ((size_t)f * S * S + (size_t)(rg.x0 + row) * S + rg.y0 + col) * 3;
+    // uint8 path: only the frames with an attempt the cluster kernel declined are packed (normally none)
+    if (only_flagged && only_flagged[f * 3].iters != KM_ITERS_FALLBACK && only_flagged[f * 3 + 1].iters != KM_ITERS_FALLBACK &&
+        only_flagged[f * 3 + 2].iters != KM_ITERS_FALLBACK)
+        return;
     char *dst = (char *)scratch + (size_t)f * scratch_stride;
-    if (F32) {
-        const float *p = (const float *)imgs + src;
-        ((float4 *)dst)[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-    } else {
-        const uint8_t *p = (const uint8_t *)imgs + src;
-        ((uchar4 *)dst)[i] = make_uchar4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rg.N; i += gridDim.x * blockDim.x) {
+        const int row = i / rg.w, col = i - row * rg.w;
+        const size_t src = ((size_t)f * S * S + (size_t)(rg.x0 + row) * S + rg.y0 + col) * 3;
+        if (F32) {
+            const float *p = (const float *)imgs + src;
+            ((float4 *)dst)[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        } else {
+            const uint8_t *p = (const uint8_t *)imgs + src;
+            ((uchar4 *)dst)[i] = make_uchar4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0);
+        }
     }
 }
 
@@ -317,9 +238,11 @@ template <bool F32, int NT>
 __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict__ scratch,
                                                                  size_t scratch_stride, int N,
                                                                  const uint64_t *__restrict__ rng_states,
-                                                                 KmAttempt *__restrict__ results)
+                                                                 KmAttempt *__restrict__ results, int only_flagged)
 {
     constexpr int NW = NT / 32;
+    // uint8 path: this kernel is the fallback of ckb_kmeans_cluster_u8 and runs only the attempts that one declined
+    if (only_flagged && results[blockIdx.y * 3 + blockIdx.x].iters != KM_ITERS_FALLBACK) return;
     // uint8 input: the labels of the current iteration are kept (1 byte per pixel, behind the packed pixels in this
     // frame's scratch slot, one array per attempt) so that the compactness pass need not recompute the three distances
     // (7 N bytes of the 16 S^2-byte slot; the pixel part is only ever read, the label part only by this CTA)
@@ -753,13 +676,32 @@ __device__ __forceinline__ int center_grey(const float *c)
     return (int)__fdiv_rn(s, 3.0f);
 }
 
-#define ZC_THREADS 1024
+#define ZC_THREADS 256
+#define ZC_SPLIT 12                    // CTAs per frame: 12 x 8 warps over the (at most) 361 zones
+
+// pixel (row i, column j of the canonical image) as float32 BGR. uint8 images are read in place; float32 images from
+// the packed scratch of ckb_pack_region (region-linear float4).
 template <bool F32>
-__global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__restrict__ scratch, size_t scratch_stride,
+__device__ __forceinline__ float3 zc_pixel(const void *base, int S, const Region &rg, int i, int j)
+{
+    if (F32) {
+        return load_px<true>(base, (i - rg.x0) * rg.w + (j - rg.y0));
+    } else {
+        const uint8_t *s = (const uint8_t *)base + ((size_t)i * S + j) * 3;
+        return make_float3((float)__ldg(s), (float)__ldg(s + 1), (float)__ldg(s + 2));
+    }
+}
+
+// grid (ZC_SPLIT, n): each CTA votes a share of the zones (one warp per zone: labels of the zone's disk against the
+// best attempt's centres, ballot-free integer histogram, ratios, colour); the last CTA of a frame to finish (ticket in
+// `tickets`, which the launcher zeroes) runs check_density over the frame's 361 stones.
+template <bool F32>
+__global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__restrict__ pixels, size_t frame_stride,
                                                                 Region rg, int gsize, int rs, int re, int cs, int ce,
                                                                 const KmAttempt *__restrict__ results,
                                                                 const int32_t *__restrict__ rects,
                                                                 const uint8_t *__restrict__ mask, int S,
+                                                                uint8_t *__restrict__ stones_ws, unsigned *__restrict__ tickets,
                                                                 uint8_t *__restrict__ stones_out,
                                                                 uint8_t *__restrict__ trusted_out,
                                                                 uint8_t *__restrict__ ratios_out,
@@ -767,11 +709,11 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
                                                                 double *__restrict__ compact_out,
                                                                 int32_t *__restrict__ labels_out)
 {
-    __shared__ uint8_t s_stones[CKB_MAX_ZONES];
     __shared__ int s_hist[3];
-    const int frame = blockIdx.x;
+    __shared__ int s_last;
+    const int frame = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const void *px = (const char *)scratch + (size_t)frame * scratch_stride;
+    const void *px = (const char *)pixels + (size_t)frame * frame_stride;
 
     // best attempt: `if (compactness < best_compactness)` in attempt order, starting from DBL_MAX
     int best = 0;
@@ -795,13 +737,12 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
     uint8_t col[3];
     for (int k = 0; k < 3; k++) col[k] = cv[k] == mn ? CKB_B : (cv[k] == mx ? CKB_W : CKB_E);
 
-    if (tid < 3) s_hist[tid] = 0;
-    if (tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         if (centers_out) for (int k = 0; k < 9; k++) centers_out[frame * 9 + k] = R.centers[k];
         if (compact_out) compact_out[frame] = bc;
     }
     const int nz = gsize * gsize;
-    for (int z = warp; z < nz; z += ZC_THREADS / 32) {
+    for (int z = blockIdx.x * (ZC_THREADS / 32) + warp; z < nz; z += ZC_SPLIT * (ZC_THREADS / 32)) {
         const int zr = z / gsize, zc = z - zr * gsize;
         uint8_t r3[3] = {0, 0, 0};
         r3[mid] = 1;
@@ -814,7 +755,7 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
                 const int i = a0 + t / zw, j = b0 + t % zw;
                 if (mask[(size_t)i * S + j]) {
                     const int li = (i - rg.x0) * rg.w + (j - rg.y0);
-                    int lab = argmin3(load_px<F32>(px, li), oc);
+                    int lab = argmin3(zc_pixel<F32>(px, S, rg, i, j), oc);
                     if (n_fix > 0 && li == f0) lab = fk0;
                     if (n_fix > 1 && li == f1) lab = fk1;
                     c0n += lab == 0;
@@ -835,7 +776,7 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
             stone = col[b];
         }
         if (lane == 0) {
-            s_stones[z] = stone;
+            stones_ws[(size_t)frame * CKB_MAX_ZONES + z] = stone;
             if (stones_out) stones_out[(size_t)frame * nz + z] = stone;
             if (ratios_out) {
                 uint8_t *o = ratios_out + ((size_t)frame * nz + z) * 3;
@@ -843,21 +784,30 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
             }
         }
     }
-    __syncthreads();
-    if (tid < nz) atomicAdd(&s_hist[s_stones[tid]], 1);
-    __syncthreads();
-    // check_density: three distinct values, each seen at least twice (sf_clustering.py:170-178)
-    if (tid == 0 && trusted_out) trusted_out[frame] = (s_hist[0] >= 2 && s_hist[1] >= 2 && s_hist[2] >= 2) ? 1 : 0;
-
     if (labels_out) {
         int32_t *lo = labels_out + (size_t)frame * rg.N;
-        for (int i = tid; i < rg.N; i += ZC_THREADS) {
-            int lab = argmin3(load_px<F32>(px, i), oc);
+        for (int i = blockIdx.x * ZC_THREADS + tid; i < rg.N; i += ZC_SPLIT * ZC_THREADS) {
+            const int row = i / rg.w, col2 = i - row * rg.w;
+            int lab = argmin3(zc_pixel<F32>(px, S, rg, rg.x0 + row, rg.y0 + col2), oc);
             if (n_fix > 0 && i == f0) lab = fk0;
             if (n_fix > 1 && i == f1) lab = fk1;
             lo[i] = lab;
         }
     }
+    // check_density: three distinct values, each seen at least twice (sf_clustering.py:170-178) — by the last CTA
+    if (!trusted_out) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        s_last = atomicAdd(&tickets[frame], 1u) == ZC_SPLIT - 1;
+        s_hist[0] = s_hist[1] = s_hist[2] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int z = tid; z < nz; z += ZC_THREADS) atomicAdd(&s_hist[__ldcg(stones_ws + (size_t)frame * CKB_MAX_ZONES + z)], 1);
+    __syncthreads();
+    if (tid == 0) trusted_out[frame] = (s_hist[0] >= 2 && s_hist[1] >= 2 && s_hist[2] >= 2) ? 1 : 0;
 }
 
 // ----------------------------------------------------------------------------------------------------------- launcher
@@ -882,11 +832,17 @@ static Region make_region(const ckb_ctx *ctx, int rs, int re, int cs, int ce)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const Region &rg, const uint64_t *d_rng_states,
+                              KmAttempt *d_results, cudaStream_t st);
+
+// workspace: [n] per-frame scratch (packed pixels + label caches of the one-CTA kernel) | [3 n] KmAttempt | [n][361]
+// stones of the zone vote | [n] tickets
 extern "C" size_t ckb_find_stones_workspace(const ckb_ctx *ctx, int n)
 {
     if (!ctx || n < 0) return 0;
     const size_t per_frame = align_up((size_t)ctx->S * ctx->S * 16, 256);
-    return (size_t)n * per_frame + align_up((size_t)n * 3 * sizeof(KmAttempt), 256) + 256;
+    return (size_t)n * per_frame + align_up((size_t)n * 3 * sizeof(KmAttempt), 256) +
+           align_up((size_t)n * CKB_MAX_ZONES, 256) + align_up((size_t)n * sizeof(unsigned), 256) + 256;
 }
 
 extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, int rs, int re, int cs, int ce,
@@ -902,36 +858,42 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
         CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: region [%d,%d)x[%d,%d) outside the %dx%d goban", rs, re, cs, ce, g, g);
     if (work_bytes < ckb_find_stones_workspace(ctx, n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_find_stones: workspace too small");
     if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: workspace must be 256-byte aligned");
-    if (n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
     CKB_ENTER(ctx, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const Region rg = make_region(ctx, rs, re, cs, ce);
     const size_t stride = align_up((size_t)ctx->S * ctx->S * 16, 256);
-    KmAttempt *res = (KmAttempt *)((char *)d_work + (size_t)n * stride);
+    char *w = (char *)d_work + (size_t)n * stride;
+    KmAttempt *res = (KmAttempt *)w;
+    w += align_up((size_t)n * 3 * sizeof(KmAttempt), 256);
+    uint8_t *stones_ws = (uint8_t *)w;
+    w += align_up((size_t)n * CKB_MAX_ZONES, 256);
+    unsigned *tickets = (unsigned *)w;
+    CKB_CUDA(ctx, cudaMemsetAsync(tickets, 0, (size_t)n * sizeof(unsigned), st));
     dim3 pgrid((rg.N + 255) / 256, n);
     if (is_f32) {
-        ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
+        ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride, nullptr);
         CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        ckb_kmeans_attempt<true, KM_THREADS_F32><<<dim3(3, n), KM_THREADS_F32, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        ckb_kmeans_attempt<true, KM_THREADS_F32><<<dim3(3, n), KM_THREADS_F32, 0, st>>>(d_work, stride, rg.N, d_rng_states, res, 0);
         CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
-        ckb_zone_classify<true><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
-                                                          ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
-                                                          d_centers, d_compactness, d_labels);
+        ckb_zone_classify<true><<<dim3(ZC_SPLIT, n), ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
+                                                                         ctx->d_mask, ctx->S, stones_ws, tickets, d_stones,
+                                                                         d_trusted, d_ratios, d_centers, d_compactness, d_labels);
         CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
     } else {
-        ckb_pack_region<false><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride);
+        // uint8 images: one thread-block cluster per (frame, attempt), pixels resident in distributed shared memory
+        // (kmeans_cluster.cu). The attempts it declines (an empty cluster; sums within reach of 2^25: pathological
+        // images) are marked in `res` and re-run by the one-CTA kernel, which otherwise exits at once.
+        const int rc = ckb_launch_kmeans_cluster(ctx, (const uint8_t *)d_imgs, n, rg, d_rng_states, res, st);
+        if (rc != CKB_OK) return rc;
+        ckb_pack_region<false><<<dim3(8, n), 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride, res);   // exits at once unless flagged
         CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        // uint8 input: the passes are parallel and bound by L2 load latency / instruction issue: wide CTAs. Measured on
-        // B200 (full board): 64 frames 1.99 / 1.52 / 1.21 ms with 256 / 512 / 1024 threads, 512 frames 5.96 / 4.64 / 5.08 ms
-        if (n <= 128)
-            ckb_kmeans_attempt<false, 1024><<<dim3(3, n), 1024, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
-        else
-            ckb_kmeans_attempt<false, 512><<<dim3(3, n), 512, 0, st>>>(d_work, stride, rg.N, d_rng_states, res);
+        ckb_kmeans_attempt<false, 1024><<<dim3(3, n), 1024, 0, st>>>(d_work, stride, rg.N, d_rng_states, res, 1);
         CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
-        ckb_zone_classify<false><<<n, ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
-                                                           ctx->d_mask, ctx->S, d_stones, d_trusted, d_ratios,
-                                                           d_centers, d_compactness, d_labels);
+        ckb_zone_classify<false><<<dim3(ZC_SPLIT, n), ZC_THREADS, 0, st>>>(d_imgs, (size_t)ctx->S * ctx->S * 3, rg, g, rs, re, cs, ce,
+                                                                          res, ctx->d_rects, ctx->d_mask, ctx->S, stones_ws,
+                                                                          tickets, d_stones, d_trusted, d_ratios, d_centers,
+                                                                          d_compactness, d_labels);
         CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
     }
     return CKB_OK;

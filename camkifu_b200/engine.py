@@ -22,9 +22,30 @@ def rng_seed(seed: int) -> int:
     return int(_lib.lib().ckb_rng_seed(seed & 0xffffffff))
 
 
+# cv::RNG is a multiply-with-carry generator: with t = carry * 2^32 + x (the 64-bit state itself), one draw is
+# t' = A * x + carry = A * t mod (A * 2^32 - 1). n draws are therefore one modular power, whatever n.
+_MWC_A = 4164903690
+_MWC_M = _MWC_A * (1 << 32) - 1
+
+
 def rng_advance(state: int, n_kmeans_calls: int) -> int:
-    """State after `n_kmeans_calls` cv2.kmeans(K=3, attempts=3, KMEANS_PP_CENTERS) calls."""
-    return int(_lib.lib().ckb_rng_advance(state, DRAWS_PER_KMEANS * n_kmeans_calls))
+    """State after `n_kmeans_calls` cv2.kmeans(K=3, attempts=3, KMEANS_PP_CENTERS) calls (39 draws each). O(log n):
+    equal to ckb_rng_advance(state, 39 n), which steps draw by draw (tests/test_abi.py checks the two against each other)."""
+    if n_kmeans_calls <= 0:
+        return int(state)
+    t = (int(state) * pow(_MWC_A, DRAWS_PER_KMEANS * int(n_kmeans_calls), _MWC_M)) % _MWC_M
+    return t if t != 0 else _MWC_M
+
+
+def rng_states(state: int, first_call: int, n: int):
+    """States before k-means calls first_call, first_call + 1, ... (n of them) of a stream that starts at `state`."""
+    step = pow(_MWC_A, DRAWS_PER_KMEANS, _MWC_M)
+    t = rng_advance(state, first_call)
+    out = []
+    for _ in range(n):
+        out.append(t)
+        t = (t * step) % _MWC_M or _MWC_M
+    return out
 
 
 class StoneEngine:
@@ -156,7 +177,14 @@ class StoneEngine:
         assert imgs.is_contiguous() and imgs.shape[1:] == (self.S, self.S, 3)
         assert imgs.dtype in (torch.uint8, torch.float32)
         n = imgs.shape[0]
-        st = torch.as_tensor(np.asarray(rng_states, dtype=np.uint64).astype(np.int64), device=self.device)
+        if isinstance(rng_states, torch.Tensor):
+            # states already on the device (int64 bit patterns): nothing is copied. A list goes through a pageable
+            # host -> device copy, which makes the driver wait for the stream first; callers that must not stall
+            # (DetectPipeline) stage their states in pinned memory and pass the device tensor.
+            st = rng_states
+            assert st.is_cuda and st.dtype == torch.int64 and st.is_contiguous()
+        else:
+            st = torch.as_tensor(np.asarray(rng_states, dtype=np.uint64).astype(np.int64), device=self.device)
         assert st.numel() == n
         dev = self.device
         out = {"stones": torch.empty((n, g, g), dtype=torch.uint8, device=dev),

@@ -10,7 +10,7 @@ Everything that computes is a kernel of libcamkifu_b200.so; torch provides buffe
 import numpy as np
 import torch
 
-from .engine import StoneEngine, rng_seed, rng_advance
+from .engine import StoneEngine, rng_seed, rng_states
 
 
 def pinned_frames(n: int, H: int, W: int) -> torch.Tensor:
@@ -20,12 +20,17 @@ def pinned_frames(n: int, H: int, W: int) -> torch.Tensor:
 
 
 class DetectPipeline:
-    """mode: "neural" (SfNeural.predict_all per frame), "clustering" (SfClustering.find_stones, full board, per frame)
-    or "both". Results are numpy arrays in pinned host memory, valid until the next call."""
+    """mode: "neural" (SfNeural.predict_all per frame), "clustering" (SfClustering.find_stones, full board, per frame),
+    "both", or "full" = everything a finder runs per frame (BASELINE.json configs[2]): warp, the MOG2 background model
+    with the reference's learning-rate schedule and the per-zone foreground counts (stonesfinder.py:171-176,
+    sf_neural.py:178-180), SfClustering's running average (sf_clustering.py:33-36), full-board find_stones and
+    predict_all. The streaming state of "full" (background model, running average, frame count) lives in the pipeline
+    and advances with every submitted frame. Results are numpy arrays in pinned host memory, valid until DEPTH more
+    batches have been submitted. `h2d_bytes` / `d2h_bytes` count everything copied since construction."""
 
     def __init__(self, H: int, W: int, gsize: int = 19, mode: str = "neural", sub_batch: int = 16, device=None,
                  cnn_params=None, engine: StoneEngine = None):
-        assert mode in ("neural", "clustering", "both")
+        assert mode in ("neural", "clustering", "both", "full")
         self.eng = engine or StoneEngine(gsize, device=device)
         self.H, self.W, self.mode, self.sub = H, W, mode, sub_batch
         dev = self.eng.device
@@ -46,6 +51,11 @@ class DetectPipeline:
         self._ticket = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        if mode == "full":
+            self.bg_state = self.eng.mog2_new_state()
+            self.accu = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+            self.d_fg = torch.empty((sub_batch, S, S), dtype=torch.uint8, device=dev)
+            self.frames_seen = 0
 
     DEPTH = 3   # batches that may be in flight (submit() without collect())
 
@@ -65,6 +75,10 @@ class DetectPipeline:
             if self.mode != "neural":
                 out["km_stones"] = torch.empty((n, g, g), dtype=torch.uint8, pin_memory=True)
                 out["km_trusted"] = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+                sl["h_states"] = torch.empty((n,), dtype=torch.int64, pin_memory=True)     # cv::RNG states, staged pinned
+                sl["d_states"] = torch.empty((n,), dtype=torch.int64, device=self.eng.device)
+            if self.mode == "full":
+                out["fg_counts"] = torch.empty((n, g, g), dtype=torch.int32, pin_memory=True)
             sl["out"], sl["cap"] = out, n
         sl["ticket"], sl["n"] = ticket, n
         return sl
@@ -86,7 +100,8 @@ class DetectPipeline:
         eng = self.eng
         roi = eng.frame_roi(mtx, self.H, self.W) if crop else None
         st0 = rng_seed(0) if rng_state is None else rng_state
-        self.h2d_bytes = self.d2h_bytes = 0
+        if self.mode != "neural":
+            sl["h_states"][:n].copy_(torch.from_numpy(np.asarray(rng_states(st0, 0, n), dtype=np.uint64).astype(np.int64)))
         if ticket == 0 or self._idle:
             cur = torch.cuda.current_stream(eng.device)
             self.copy_stream.wait_stream(cur)
@@ -106,14 +121,24 @@ class DetectPipeline:
                 self.comp_stream.wait_event(self.ev_up[b])
                 goban = eng.warp(self.d_frames[b][:m], mtx, out=self.d_goban[:m])
                 self.ev_free[b].record(self.comp_stream)
+                if self.mode == "full":
+                    t0 = self.frames_seen     # stonesfinder.py:171-176: rate 0.01 while learning (bg_init_frames = 50), then 0.005
+                    fg = eng.mog2_apply(goban, self.bg_state, t0, [0.01 if t0 + i < 50 else 0.005 for i in range(m)],
+                                        out=self.d_fg[:m])
+                    cnt = eng.zone_fg_counts(fg)
+                    out["fg_counts"][f0:f0 + m].copy_(cnt, non_blocking=True)
+                    self.d2h_bytes += cnt.numel() * 4
+                    eng.accumulate(goban, self.accu, first=(t0 == 0))
+                    self.frames_seen = t0 + m
                 if self.mode != "clustering":
                     r = eng.cnn_forward(goban, want_softmax=False)
                     for name in ("stones", "keep", "conf"):
                         out[name][f0:f0 + m].copy_(r[name], non_blocking=True)
                         self.d2h_bytes += r[name].numel() * r[name].element_size()
                 if self.mode != "neural":
-                    states = [rng_advance(st0, f0 + i) for i in range(m)]
-                    r = eng.find_stones(goban, states)
+                    if f0 == 0:
+                        sl["d_states"][:n].copy_(sl["h_states"][:n], non_blocking=True)
+                    r = eng.find_stones(goban, sl["d_states"][f0:f0 + m])
                     out["km_stones"][f0:f0 + m].copy_(r["stones"], non_blocking=True)
                     out["km_trusted"][f0:f0 + m].copy_(r["trusted"], non_blocking=True)
                     self.d2h_bytes += r["stones"].numel() + r["trusted"].numel()

@@ -35,8 +35,8 @@ def kmeans_calls_before(frame: int, every: int = 3) -> int:
 
 def rng_state_at(state0: int, frame: int, every: int = 3) -> int:
     """cv::RNG state at the k-means call of `frame`, given the state before frame 0."""
-    from . import _lib
-    return int(_lib.lib().ckb_rng_advance(state0, DRAWS_PER_KMEANS * kmeans_calls_before(frame, every)))
+    from .engine import rng_advance
+    return rng_advance(state0, kmeans_calls_before(frame, every))
 
 
 def gather_board_states(local, n_frames: int, align: int = 3, group=None):

@@ -49,6 +49,11 @@ def test_rng_and_inverse_helpers(oracle):
     st0 = oracle.rng_seed_state(7)
     _, _, _, st1, _ = oracle.c_kmeans(px, st0)
     assert L.ckb_rng_advance(st0, 39) == st1
+    # the host-side jump-ahead (one modular power) against stepping draw by draw
+    from camkifu_b200.engine import rng_advance, rng_states
+    for n in (0, 1, 2, 3, 50, 1234):
+        assert rng_advance(st0, n) == L.ckb_rng_advance(st0, 39 * n)
+    assert rng_states(st0, 5, 4) == [L.ckb_rng_advance(st0, 39 * (5 + i)) for i in range(4)]
     rng = np.random.default_rng(1)
     for _ in range(200):
         M = rng.normal(size=(3, 3)) * np.array([[1, 1, 500], [1, 1, 500], [1e-3, 1e-3, 1]])
