@@ -20,7 +20,7 @@ if sys.argv[1:] == ["build"]:
     from camkifu_b200 import build
     os.makedirs(os.path.join(PROBE, "obj"), exist_ok=True)
     for v in VARIANTS:
-        print(build.build(force=True, extra_flags=["-DKC_TIMING", "-DKC_EXP=%d" % v], out=LIB.replace(".so", "%d.so" % v),
+        print(build.build(force=True, extra_flags=(["-DKC_TIMING"] if os.environ.get("KC_TIMING", "1") == "1" else []) + ["-DKC_EXP=%d" % v], out=LIB.replace(".so", "%d.so" % v),
                           bdir=os.path.join(PROBE, "obj")))
     sys.exit(0)
 
@@ -29,7 +29,8 @@ if sys.argv[1:] == ["run"]:     # the instrumented library prints from the kerne
         print("---- KC_EXP =", v, flush=True)
         env = dict(os.environ, CAMKIFU_B200_LIB=LIB.replace(".so", "%d.so" % v))
         subprocess.run([sys.executable, __file__, "child", "1"], env=env, check=False)
-    subprocess.run([sys.executable, __file__, "child", "0"], check=False)
+    if os.environ.get("KC_TIMING", "1") == "1":
+        subprocess.run([sys.executable, __file__, "child", "0"], check=False)
     sys.exit(0)
 
 import numpy as np  # noqa: E402
