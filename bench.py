@@ -172,7 +172,7 @@ class CpuPath:
         return statistics.median(vals)
 
 
-def cpu_baseline_block(frames, mtx, params):
+def cpu_baseline_block(frames, mtx, params, video_file=None):
     threads = os.cpu_count() or 1
     cp = CpuPath(params, threads)
     cp.mtx = mtx
@@ -186,6 +186,21 @@ def cpu_baseline_block(frames, mtx, params):
                           "sample": "16 frames x 3, median; warp + MOG2 + running average + cv2.kmeans full board + "
                                     "361-zone np.unique loop + CNN (config 3)"},
     }
+    if video_file:
+        import cv2
+        n_v, t0 = 0, time.perf_counter()
+        for _ in range(1):                      # the 512-frame file once
+            cap = cv2.VideoCapture(video_file)
+            while True:
+                ok, fr = cap.read()
+                if not ok:
+                    break
+                cp.neural(fr, mtx)
+                n_v += 1
+            cap.release()
+        variants["video_file"] = {"value": n_v / (time.perf_counter() - t0), "threads": threads,
+                                  "sample": "%d frames: cv2.VideoCapture.read (MJPG 1080p) + warp + CNN + decode per frame, "
+                                            "the reference's CaptureReader pattern without its 5 fps throttle" % n_v}
     cp1 = CpuPath(params, 1)
     cp1.mtx = mtx
     variants["neural_1_thread"] = {"value": cp1.fps(cp1.neural, frames, 16, 5), "threads": 1,
@@ -301,17 +316,39 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         eng.warp(resident[i % n_rot], mtx, out=goban)
         return eng.cnn_forward(goban, want_softmax=False)
 
-    def step_full(i):
-        f0 = full_state["frames"]
-        eng.warp(resident[i % n_rot], mtx, out=goban)
+    side = torch.cuda.Stream(device=dev)
+    ev_warped, ev_side = torch.cuda.Event(), torch.cuda.Event()
+
+    def stats_branch(f0):
         eng.mog2_apply(goban, bg, f0, 0.01 if f0 + BATCH <= 50 else [0.01 if f0 + k < 50 else 0.005 for k in range(BATCH)],
                        out=fg)
         cnt = eng.zone_fg_counts(fg)
         eng.accumulate(goban, accu, first=(f0 == 0))
-        km = eng.find_stones(goban, km_states_dev)
-        nn = eng.cnn_forward(goban, want_softmax=False)
+        return eng.find_stones(goban, km_states_dev), cnt
+
+    def step_full(i, overlap=True):
+        """one 64-frame batch through everything. overlap: the background / running-average / k-means branch runs on a
+        second stream next to the CNN branch (both only read the canonical images), as DetectPipeline(mode="full") does;
+        the serial form exists for the per-kernel timing, whose events need one stream."""
+        f0 = full_state["frames"]
+        eng.warp(resident[i % n_rot], mtx, out=goban)
+        if overlap:
+            cur = torch.cuda.current_stream()
+            ev_warped.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_warped)
+                km, cnt = stats_branch(f0)
+                ev_side.record(side)
+            nn = eng.cnn_forward(goban, want_softmax=False)
+            cur.wait_event(ev_side)
+        else:
+            km, cnt = stats_branch(f0)
+            nn = eng.cnn_forward(goban, want_softmax=False)
         full_state["frames"] = f0 + BATCH
         return nn, km, cnt
+
+    def step_full_serial(i):
+        return step_full(i, overlap=False)
 
     def barrier():
         if world > 1:
@@ -409,10 +446,11 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
 
     # ---- leg A: headline (config 2), burst over K steps
     ms_total, prof, launches, clocks, out = timed_steps(step_neural, args.steps, args.warmup, gather=True)
-    # ---- leg B: the same step sustained
+    # ---- leg C: the whole pipeline (config 3), burst (before the sustained legs, which leave the GPU power-capped)
+    pipe_ms, _, pipe_launches, pipe_clocks, pipe_out = timed_steps(step_full, args.steps, args.warmup, profile=False)
+    pser_ms, pipe_prof, _, _, _ = timed_steps(step_full_serial, args.steps, 1)       # one stream: per-kernel times
+    # ---- legs B / D: both steps sustained
     sus_ms, sus_n, sus_clocks = sustained(step_neural)
-    # ---- leg C / D: the whole pipeline (config 3), burst and sustained
-    pipe_ms, pipe_prof, pipe_launches, pipe_clocks, pipe_out = timed_steps(step_full, args.steps, args.warmup)
     psus_ms, psus_n, psus_clocks = sustained(step_full)
 
     # ---- host -> device ceiling of this job: every rank copies a pinned 256 MB buffer at the same time
@@ -452,13 +490,59 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     pe2e_ok = bool(np.array_equal(pres["km_stones"], pipe_out[1]["stones"].cpu().numpy()) and
                    np.array_equal(pres["stones"], pipe_out[0]["stones"].cpu().numpy()))
 
+    # ---- offline video (BASELINE.json configs[4]): process_video = decode -> pinned ring -> detect_stream, the frames
+    # of one video sharded over the ranks, one final gather. (i) a long clip held in host memory (what the path behind the
+    # decoder sustains), (ii) an encoded 1080p file decoded on the host by several threads per rank.
+    from camkifu_b200.video import FrameSource, RingClip, process_video
+    vpipe = DetectPipeline(H, W, GSIZE, mode="neural", sub_batch=16, engine=eng)
+    vmem_frames = args.video_frames * world
+    cores = os.cpu_count() or 1
+    decoders = max(1, min(8, cores // world - 1))
+    vfile = os.path.join("/tmp", "ckb_bench_%s.avi" % os.environ.get("MASTER_PORT", "single"))
+    vfile_frames = 512
+    if rank == 0:
+        import cv2
+        wr = cv2.VideoWriter(vfile, cv2.VideoWriter_fourcc(*"MJPG"), 30, (W, H))
+        for i in range(vfile_frames):
+            wr.write(frames_np[i % BATCH])
+        wr.release()
+    process_video(RingClip(host, 4 * BATCH * world), mtx, mode="neural", batch=BATCH, pipeline=vpipe)     # warm-up
+    barrier()
+
+    def timed_video(source, dec, vbatch):
+        stats = {}
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        out_v = process_video(source, mtx, mode="neural", batch=vbatch, pipeline=vpipe, decoders=dec, depth=3, stats=stats)
+        v1.record()
+        barrier()
+        return v0.elapsed_time(v1) / 1e3, out_v["stones"].shape[0], stats["frames"]
+
+    vmem_s, vmem_n, _ = timed_video(RingClip(host, vmem_frames), 1, BATCH)
+    # decode alone first (this rank's shard of the file, no GPU work): it names the limiter of the file leg, and it
+    # page-locks the decoders' batch buffers (slow, cached by torch afterwards) outside the timed leg
+    a_f, b_f = __import__("camkifu_b200.sharding", fromlist=["shard_range"]).shard_range(vfile_frames, rank, world)
+    vdec_s = None
+    for _ in range(2):
+        barrier()
+        td = time.perf_counter()
+        fs = FrameSource(vfile, a_f, b_f, batch=16, depth=3, decoders=decoders)
+        for buf_v, m_v, pos_v in fs:
+            fs.release(buf_v)
+        vdec_s = time.perf_counter() - td
+        del fs
+    barrier()
+    vfile_s, vfile_n, vfile_mine = timed_video(vfile, decoders, 16)
+
     # ---- max over ranks
-    t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms = (float(v) for v in t)
+    ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s = (float(v) for v in t)
     if rank != 0:
         return
+
     fps = lambda steps, ms: world * BATCH * steps / (ms / 1e3)   # noqa: E731
     value = fps(args.steps, ms_total)
     h2d_peak = world * 8 * (256 << 20) / (h2d_ms / 1e3) / 1e9
@@ -508,11 +592,15 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     # ---- CPU baseline on this host (bounded samples; rank 0 of the N = 1 run only)
     threads = os.cpu_count() or 1
     if world == 1:
-        cpu_line = cpu_baseline_block(frames_np, mtx, params)
+        cpu_line = cpu_baseline_block(frames_np, mtx, params, video_file=vfile)
     else:
         cpu_line = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": "not timed at N > 1: see the N = 1 line and --impl reference"}
 
+    try:
+        os.remove(vfile)
+    except OSError:
+        pass
     e2e_value = fps(args.steps, e2e_s * 1e3)
     pe2e_value = fps(args.steps, pe2e_s * 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -538,6 +626,9 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
             "cnn": {"tflops_algorithmic": cnn_flop / (cnn_ms * 1e-3) / 1e12, "ms_per_step": cnn_ms},
             "pipeline": {"workload": PIPE_WORKLOAD, "value": fps(args.steps, pipe_ms), "unit": UNIT,
                          "ms_per_step": pipe_ms / args.steps, "gpu_launches": pipe_launches, "clocks": pipe_clocks,
+                         "streams": "two: background model + running average + k-means next to the CNN (both read the warped "
+                                    "images); `kernels` below are timed in a separate single-stream run (%.3f ms per step)"
+                                    % (pser_ms / args.steps),
                          "value_sustained": {"value": fps(psus_n, psus_ms), "steps": psus_n, "seconds": psus_ms / 1e3,
                                              "clocks": psus_clocks},
                          "e2e": {"value": pe2e_value, "unit": UNIT, "h2d_bytes_per_step": ph2d, "d2h_bytes_per_step": pd2h,
@@ -545,6 +636,20 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
                                  "matches_resident_path": pe2e_ok, "h2d_gbs": world * ph2d * args.steps / pe2e_s / 1e9},
                          "kernels": kernel_rows(pagg, args.steps),
                          "real_time_factor_at_30fps": fps(psus_n, psus_ms) / 30.0},
+            "video": {"workload": "offline video processing, synthetic 1080p frames sharded over %d GPU(s) by frame range "
+                                  "(sharding.shard_range), one final gather of the per-frame board states "
+                                  "(BASELINE.json configs[4]); SfNeural predict_all per frame" % world,
+                      "api": "camkifu_b200.video.process_video",
+                      "memory": {"value": vmem_n / vmem_s, "unit": UNIT, "frames": vmem_n, "seconds": vmem_s,
+                                 "source": "RingClip: a %d-frame video held in pinned host memory as a 64-frame ring "
+                                           "(no decoder)" % vmem_n,
+                                 "limiter": "host -> device copies (PCIe): %.1f of the %.1f GB/s this job measured"
+                                            % (vmem_n * h2d / BATCH / vmem_s / 1e9, h2d_peak)},
+                      "file": {"value": vfile_n / vfile_s, "unit": UNIT, "frames": vfile_n, "seconds": vfile_s,
+                               "source": "MJPG 1080p .avi written by rank 0 (%d frames), OpenCV/FFmpeg decode on the host, "
+                                         "%d decoder threads per rank straight into pinned slots" % (vfile_frames, decoders),
+                               "decode_only_fps": vfile_n / vdec_s, "host_cores": cores,
+                               "limiter": "host decode" if vfile_n / vdec_s < 0.8 * vmem_n / vmem_s else "host -> device copies"}},
             "parity_check": check}
     print(json.dumps(line), flush=True)
 
@@ -555,6 +660,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--video-frames", type=int, default=20480, help="frames per rank of the in-memory offline-video leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -112,6 +112,11 @@ extern "C" int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, i
     int y0 = 0, y1 = H, x0 = 0, x1 = W;
     if (roi4) { y0 = roi4[0]; y1 = roi4[1]; x0 = roi4[2]; x1 = roi4[3]; }
     if (y0 < 0 || x0 < 0 || y1 > H || x1 > W) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: roi outside the frame");
+    // same pitch rules as ckb_warp, for both sides: rows hold W pixels, frames hold H rows
+    if (h_row_pitch < (size_t)W * 3 || d_row_pitch < (size_t)W * 3)
+        CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: row pitch smaller than a row (%d pixels)", W);
+    if (n > 1 && (h_frame_pitch < h_row_pitch * (size_t)H || d_frame_pitch < d_row_pitch * (size_t)H))
+        CKB_FAIL(ctx, CKB_E_INVALID, "ckb_upload_frames: frame pitch smaller than a frame (%d rows)", H);
     if (y1 <= y0 || x1 <= x0 || n == 0) return CKB_OK;
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t wbytes = (size_t)(x1 - x0) * 3;

@@ -53,7 +53,9 @@ __device__ __forceinline__ void load_row_taps(const uint8_t *frame, size_t row_p
     hi = 0;
     if ((unsigned)sy >= (unsigned)H) return;
     const uint8_t *row = frame + (size_t)sy * row_pitch;
-    if (sx >= 0 && sx + 1 < W) {
+    // load6 reads the aligned words around the 6 bytes it needs (up to 3 bytes before and after them): not where that
+    // window could leave the frame (its first bytes, the end of its last row)
+    if (sx >= 0 && sx + 1 < W && (sy > 0 || sx > 0) && (sy + 1 < H || sx + 3 <= W)) {
         load6(row + (size_t)sx * 3, lo, hi);
         hi &= 0xffffu;
     } else {

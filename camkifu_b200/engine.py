@@ -55,10 +55,12 @@ class StoneEngine:
         self.L = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
             if not isinstance(device, torch.device) else device
+        if self.device.index is None:       # torch.device("cuda"): the context must bind to the device tensors live on
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.gsize = gsize
         self.S = 20 * gsize
         h = C.c_void_p()
-        rc = self.L.ckb_create(C.byref(h), self.device.index or 0, gsize)
+        rc = self.L.ckb_create(C.byref(h), self.device.index, gsize)
         self._h = h
         if rc != 0:
             msg = self.L.ckb_last_error(h).decode() if h else "ckb_create failed"
@@ -88,10 +90,15 @@ class StoneEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _workspace(self, nbytes: int) -> torch.Tensor:
-        if self._work is None or self._work.numel() < nbytes:
-            self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._work
+    def _workspace(self, nbytes: int, key: str = "cnn") -> torch.Tensor:
+        """Scratch buffers, one per kernel family: the k-means and the CNN branches of a frame batch may run on two
+        streams at once (DetectPipeline, bench.py), so they must not share one."""
+        if self._work is None:
+            self._work = {}
+        w = self._work.get(key)
+        if w is None or w.numel() < nbytes:
+            w = self._work[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return w
 
     @property
     def launches(self) -> int:
@@ -201,7 +208,7 @@ class StoneEngine:
             y1 = self.S - 1 if ce == g else 20 * ce
             out["labels"] = torch.empty((n, x1 - x0, y1 - y0), dtype=torch.int32, device=dev)
         wb = self.L.ckb_find_stones_workspace(self._h, n)
-        work = self._workspace(wb)
+        work = self._workspace(wb, "kmeans")
         self._check(self.L.ckb_find_stones(self._h, self._ptr(imgs), int(imgs.dtype == torch.float32), n, rs, re, cs,
                                            ce, self._ptr(st), self._ptr(work), work.numel(), self._ptr(out["stones"]),
                                            self._ptr(out["trusted"]), self._ptr(out.get("ratios")),
@@ -229,7 +236,7 @@ class StoneEngine:
         if want_softmax:
             out["softmax"] = torch.empty((n, 100, 81), dtype=torch.float32, device=dev)
         wb = (self.L.ckb_cnn_workspace_simt if simt else self.L.ckb_cnn_workspace)(self._h, n)
-        work = self._workspace(wb)
+        work = self._workspace(wb, "cnn")
         fn = self.L.ckb_cnn_forward_simt if simt else self.L.ckb_cnn_forward
         self._check(fn(self._h, self._ptr(goban), n, self._ptr(work), work.numel(), self._ptr(out.get("softmax")),
                        self._ptr(out["stones"]), self._ptr(out["conf"]), self._ptr(out["keep"]), self._stream()))
@@ -243,7 +250,7 @@ class StoneEngine:
         """Test aid: dense float32 copy of an intermediate activation of the last cnn_forward (n <= 64 frames)."""
         shape = {1: (36, 36, 32), 2: (16, 16, 32), 3: (14, 14, 90), 5: (160,)}[layer]
         out = torch.zeros((n * 100,) + shape, dtype=torch.float32, device=self.device)
-        self._check(self.L.ckb_cnn_debug_activation(self._h, self._ptr(self._work), n, layer, self._ptr(out),
+        self._check(self.L.ckb_cnn_debug_activation(self._h, self._ptr(self._work["cnn"]), n, layer, self._ptr(out),
                                                     self._stream()))
         return out
 

@@ -44,6 +44,8 @@ class DetectPipeline:
         self.d_goban = torch.empty((sub_batch, S, S, 3), dtype=torch.uint8, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.comp_stream = torch.cuda.Stream(device=dev)
+        self.side_stream = torch.cuda.Stream(device=dev)      # mode "full": the statistics branch next to the CNN branch
+        self.ev_warped, self.ev_side = torch.cuda.Event(), torch.cuda.Event()
         self.ev_up = [torch.cuda.Event() for _ in range(2)]
         self.ev_free = [torch.cuda.Event() for _ in range(2)]
         self._k = 0                     # sub-batches enqueued so far (the device frame buffers are a ring of two)
@@ -121,27 +123,38 @@ class DetectPipeline:
                 self.comp_stream.wait_event(self.ev_up[b])
                 goban = eng.warp(self.d_frames[b][:m], mtx, out=self.d_goban[:m])
                 self.ev_free[b].record(self.comp_stream)
+                # the statistics branch (background model, running average, k-means) and the CNN branch both only read
+                # the warped images: in mode "full" the first runs on a side stream next to the second
+                stats_stream = self.side_stream if self.mode == "full" else self.comp_stream
                 if self.mode == "full":
-                    t0 = self.frames_seen     # stonesfinder.py:171-176: rate 0.01 while learning (bg_init_frames = 50), then 0.005
-                    fg = eng.mog2_apply(goban, self.bg_state, t0, [0.01 if t0 + i < 50 else 0.005 for i in range(m)],
-                                        out=self.d_fg[:m])
-                    cnt = eng.zone_fg_counts(fg)
-                    out["fg_counts"][f0:f0 + m].copy_(cnt, non_blocking=True)
-                    self.d2h_bytes += cnt.numel() * 4
-                    eng.accumulate(goban, self.accu, first=(t0 == 0))
-                    self.frames_seen = t0 + m
+                    self.ev_warped.record(self.comp_stream)
+                    self.side_stream.wait_event(self.ev_warped)
+                with torch.cuda.stream(stats_stream):
+                    if self.mode == "full":
+                        t0 = self.frames_seen     # stonesfinder.py:171-176: rate 0.01 while learning (bg_init_frames = 50), then 0.005
+                        fg = eng.mog2_apply(goban, self.bg_state, t0, [0.01 if t0 + i < 50 else 0.005 for i in range(m)],
+                                            out=self.d_fg[:m])
+                        cnt = eng.zone_fg_counts(fg)
+                        out["fg_counts"][f0:f0 + m].copy_(cnt, non_blocking=True)
+                        self.d2h_bytes += cnt.numel() * 4
+                        eng.accumulate(goban, self.accu, first=(t0 == 0))
+                        self.frames_seen = t0 + m
+                    if self.mode != "neural":
+                        if f0 == 0:
+                            sl["d_states"][:n].copy_(sl["h_states"][:n], non_blocking=True)
+                        r = eng.find_stones(goban, sl["d_states"][f0:f0 + m])
+                        out["km_stones"][f0:f0 + m].copy_(r["stones"], non_blocking=True)
+                        out["km_trusted"][f0:f0 + m].copy_(r["trusted"], non_blocking=True)
+                        self.d2h_bytes += r["stones"].numel() + r["trusted"].numel()
+                    if self.mode == "full":
+                        self.ev_side.record(self.side_stream)
                 if self.mode != "clustering":
                     r = eng.cnn_forward(goban, want_softmax=False)
                     for name in ("stones", "keep", "conf"):
                         out[name][f0:f0 + m].copy_(r[name], non_blocking=True)
                         self.d2h_bytes += r[name].numel() * r[name].element_size()
-                if self.mode != "neural":
-                    if f0 == 0:
-                        sl["d_states"][:n].copy_(sl["h_states"][:n], non_blocking=True)
-                    r = eng.find_stones(goban, sl["d_states"][f0:f0 + m])
-                    out["km_stones"][f0:f0 + m].copy_(r["stones"], non_blocking=True)
-                    out["km_trusted"][f0:f0 + m].copy_(r["trusted"], non_blocking=True)
-                    self.d2h_bytes += r["stones"].numel() + r["trusted"].numel()
+                if self.mode == "full":
+                    self.comp_stream.wait_event(self.ev_side)      # the next warp overwrites the images both branches read
         sl["done"].record(self.comp_stream)
         return ticket
 

@@ -5,13 +5,16 @@ find_stones on a given image, predict_all), so each rank takes a contiguous fram
 final gather of per-frame board states (uint8 [n, 361] — 36 MB per 100 k frames). Streaming state is handled per shard:
   * the every-third-frame cadence of SfClustering._find (sf_clustering.py:37): shard starts are multiples of 3;
   * cv2's process-global RNG carried across k-means calls: `rng_state_at` replays the draw count (39 per call);
-  * the running average (alpha = 0.2): `halo` frames before the shard start warm it up (0.8^80 < 2^-24).
+  * the running average (alpha = 0.2): `halo` frames before the shard start warm it up. The restarted float32 recurrence
+    converges to the streaming one geometrically (255 x 0.8^120 = 6e-10, below half an ulp of every accumulator value
+    above 0.01), after which the two are equal bit for bit in practice (tests/test_sharding.py compares them); it is a
+    convergence argument, not an identity: callers that need a guarantee hand the accumulator itself across the seam.
 """
 import numpy as np
 
 from .engine import DRAWS_PER_KMEANS
 
-ACCU_HALO = 80
+ACCU_HALO = 120
 
 
 def shard_range(n_frames: int, rank: int, world: int, align: int = 3):
@@ -55,3 +58,23 @@ def gather_board_states(local, n_frames: int, align: int = 3, group=None):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([parts[r][:b - a] for r, (a, b) in enumerate(ranges)], dim=0)
+
+
+def gather_ragged(local, group=None):
+    """All ranks -> the concatenation, in rank order, of every rank's [k_r, ...] tensor (k_r may differ and be zero), on
+    every rank: the ranks first agree on the counts, so a rank that got fewer frames than planned (a video file shorter
+    than its header says) cannot stall the others."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
+    counts = [int(c) for c in counts]
+    longest = max(max(counts), 1)
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][:counts[r]] for r in range(world)], dim=0)

@@ -3,11 +3,16 @@
 The reference reads a file through `CaptureReader` (src/camkifu/core/vmanager.py:510-525,563-586): one `VideoCapture.read`
 per processed frame on the finder's thread, throttled to `file_fps` = 5 frames per second of video by skipping frames
 (cvconf.py:18-19). This module is the ingest side of the batch path that replaces that cadence ("fast video file
-processing", README.md:35): every frame of [start, stop) is decoded by a background thread straight
-into page-locked batch buffers while the previous batches upload and compute, and with several processes (one per GPU)
-each rank takes a contiguous frame range (camkifu_b200.sharding) and the per-frame board states are gathered once at the
-end. Decoding is OpenCV's FFmpeg reader on the host (this image has no NVDEC binding); at 1080p it, not the GPU, sets the
-pace of a single process — which is why the shards matter.
+processing", README.md:35): every frame of [start, stop) is decoded by background threads straight
+into page-locked batch buffers (`VideoCapture.read(image=slot)`: no intermediate copy) while the previous batches upload
+and compute; with several processes (one per GPU) each rank takes a contiguous frame range (camkifu_b200.sharding) and
+the per-frame board states are gathered once at the end. Decoding is OpenCV's FFmpeg reader on the host (this image has no
+NVDEC binding: see DESIGN.md for the probe); at 1080p it, not the GPU, sets the pace, which is why a rank may run several
+decoder threads (`decoders`), each with its own capture over a contiguous part of the rank's range.
+
+Frame counts. FFmpeg only estimates `CAP_PROP_FRAME_COUNT` for many containers, so a failed read is the end of the stream,
+not an error: the decoder stops, the rank returns the frames it really got, and the ranks agree on the real counts before
+the final gather (which therefore cannot dead-lock on a short file).
 
 Nothing here computes on the detection path: frames go to `DetectPipeline` untouched.
 """
@@ -22,7 +27,8 @@ from .pipeline import DetectPipeline, pinned_frames
 
 
 def open_source(source):
-    """(capture or array, n_frames, H, W) of a video file path or an indexable of BGR uint8 frames."""
+    """(capture or indexable, n_frames, H, W) of a video file path or an indexable of BGR uint8 frames. For a file
+    n_frames is the container's estimate."""
     if isinstance(source, str):
         import cv2
         cap = cv2.VideoCapture(source)
@@ -33,69 +39,148 @@ def open_source(source):
     return source, len(source), int(source[0].shape[0]), int(source[0].shape[1])
 
 
-class FrameSource:
-    """Frames [start, stop) of a video as pinned batches, decoded by a daemon thread. `source` is a file path
-    (cv2.VideoCapture) or any indexable of BGR uint8 frames (e.g. a numpy array [n, H, W, 3]). Iterating yields
-    (pinned buffer [batch, H, W, 3], frames filled m, index of the first frame); the consumer hands every buffer back
-    with `release()` once the batch has been consumed (its upload has completed), and the decoder blocks when all
-    `depth` buffers are out."""
+def probe(source):
+    """(n_frames, H, W) without keeping a capture open."""
+    src, n, H, W = open_source(source)
+    if isinstance(source, str):
+        src.release()
+    return n, H, W
 
-    def __init__(self, source, start: int = 0, stop: int = None, batch: int = 32, depth: int = 5):
-        src, self.n_total, self.H, self.W = open_source(source)
-        self._cap = src if isinstance(source, str) else None
-        self._arr = None if isinstance(source, str) else src
+
+class RingClip:
+    """A long synthetic video held in host memory as a short ring: frame i is ring[i % len(ring)]. `ring` is a pinned
+    torch tensor [k, H, W, 3]; FrameSource hands out views of it (no copy), so this source measures the path behind the
+    decoder. Batches never straddle the end of the ring."""
+
+    def __init__(self, ring: torch.Tensor, n_frames: int):
+        assert ring.dim() == 4 and ring.dtype == torch.uint8
+        self.ring, self.n = ring, int(n_frames)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.ring[i % self.ring.shape[0]].numpy()
+
+    def view(self, pos: int, m: int):
+        k = self.ring.shape[0]
+        a = pos % k
+        m = min(m, k - a)
+        return self.ring[a:a + m], m
+
+
+class FrameSource:
+    """Frames [start, stop) of a video as pinned batches. `source` is a file path (cv2.VideoCapture), any indexable of
+    BGR uint8 frames (e.g. a numpy array [n, H, W, 3]) or a RingClip. Iterating yields (pinned buffer [batch, H, W, 3],
+    frames filled m, index of the first frame); the consumer hands every buffer back with `release()` once the batch has
+    been consumed (its upload has completed), and a decoder blocks when all its `depth` buffers are out.
+
+    decoders = 1: batches come in frame order. decoders = k > 1: k threads, each with its own capture over a contiguous
+    part of the range; batches are yielded as they complete, so their order interleaves the parts (every batch carries
+    its first frame index) — for consumers whose result does not depend on the order of the frames."""
+
+    def __init__(self, source, start: int = 0, stop: int = None, batch: int = 32, depth: int = 5, decoders: int = 1):
+        self.source = source
+        self.n_total, self.H, self.W = probe(source)
         self.start = max(0, start)
         self.stop = self.n_total if stop is None else min(stop, self.n_total)
         self.batch = batch
-        self._free = queue.Queue()
-        for _ in range(depth):
-            self._free.put(pinned_frames(batch, self.H, self.W))
+        self.frames_read = 0                 # frames really delivered (a file may be shorter than its header says)
+        self._ring = source if isinstance(source, RingClip) else None
+        self._is_file = isinstance(source, str)
         self._q = queue.Queue()
         self._err = None
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        self._threads = []
+        self._free = {}
+        n = max(0, self.stop - self.start)
+        k = max(1, min(decoders, (n + batch - 1) // batch)) if (self._is_file and n) else 1
+        per = ((n + k - 1) // k + batch - 1) // batch * batch if n else 0      # whole batches per decoder
+        self._pending = k
+        self._lock = threading.Lock()
+        for j in range(k):
+            a = self.start + j * per
+            b = min(self.stop, a + per)
+            fq = queue.Queue()
+            if self._ring is None:
+                for _ in range(depth):
+                    buf = pinned_frames(batch, self.H, self.W)
+                    self._free[buf.data_ptr()] = fq
+                    fq.put(buf)
+            t = threading.Thread(target=self._run, args=(a, b, fq), daemon=True)
+            self._threads.append(t)
+            t.start()
 
     def __len__(self):
         return max(0, self.stop - self.start)
 
     def release(self, buf):
-        self._free.put(buf)
+        fq = self._free.get(buf.data_ptr())
+        if fq is not None:                   # views of a RingClip are not recycled
+            fq.put(buf)
 
-    def _seek(self):
+    @staticmethod
+    def _seek(cap, start):
         import cv2
-        cap = self._cap
-        if self.start == 0:
+        if start == 0:
             return
-        cap.set(cv2.CAP_PROP_POS_FRAMES, self.start)
-        if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != self.start:      # inexact seek (inter-frame codec): walk there
+        cap.set(cv2.CAP_PROP_POS_FRAMES, start)
+        if int(cap.get(cv2.CAP_PROP_POS_FRAMES)) != start:      # inexact seek (inter-frame codec): walk there
             cap.set(cv2.CAP_PROP_POS_FRAMES, 0)
-            for _ in range(self.start):
+            for _ in range(start):
                 if not cap.grab():
                     break
 
-    def _run(self):
+    def _run(self, a, b, fq):
+        cap = None
         try:
-            if self._cap is not None:
-                self._seek()
-            pos = self.start
-            while pos < self.stop:
-                buf = self._free.get()
-                m = min(self.batch, self.stop - pos)
+            if self._is_file:
+                import cv2
+                cap = cv2.VideoCapture(self.source)
+                if not cap.isOpened():
+                    raise IOError("cannot open video " + self.source)
+                self._seek(cap, a)
+            pos = a
+            while pos < b:
+                m = min(self.batch, b - pos)
+                if self._ring is not None:
+                    buf, m = self._ring.view(pos, m)
+                    self._q.put((buf, m, pos))
+                    pos += m
+                    continue
+                buf = fq.get()
                 view = buf.numpy()
+                got = 0
                 for i in range(m):
-                    if self._cap is not None:
-                        ok, frame = self._cap.read()
+                    if cap is not None:
+                        dst = view[i]
+                        ok, frame = cap.read(dst)              # decode straight into the pinned slot
                         if not ok:
-                            raise IOError("decode failed at frame %d" % (pos + i))
-                        view[i] = frame
+                            break                              # end of the stream (the header's count was an estimate)
+                        if frame.ctypes.data != dst.ctypes.data:
+                            dst[...] = frame                   # OpenCV allocated its own image: copy it in
                     else:
-                        view[i] = self._arr[pos + i]
-                self._q.put((buf, m, pos))
-                pos += m
+                        try:
+                            view[i] = self.source[pos + i]
+                        except IndexError:                     # shorter than len() claimed: same rule as for files
+                            break
+                    got += 1
+                if got:
+                    self._q.put((buf, got, pos))
+                else:
+                    fq.put(buf)
+                pos += got
+                if got < m:
+                    break
         except BaseException as e:   # surfaced on the consumer side
             self._err = e
         finally:
-            self._q.put(None)
+            if cap is not None:
+                cap.release()
+            with self._lock:
+                self._pending -= 1
+                last = self._pending == 0
+            if last:
+                self._q.put(None)
 
     def __iter__(self):
         while True:
@@ -104,53 +189,64 @@ class FrameSource:
                 if self._err is not None:
                     raise self._err
                 return
+            self.frames_read += item[1]
             yield item
 
 
 def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int = 32, cnn_params=None, engine=None,
-                  rng_state: int = None, rank: int = None, world: int = None, gather: bool = True, pipeline=None):
+                  rng_state: int = None, rank: int = None, world: int = None, gather: bool = True, pipeline=None,
+                  decoders: int = 1, depth: int = 3, stats: dict = None):
     """Board states of every frame of a video under one board homography `mtx` (a fixed camera: the reference's manual
     board finder). Returns {name: array [n_frames, ...]} — "stones"/"keep"/"conf" (neural), "km_stones"/"km_trusted"
     (clustering: full-board find_stones per frame, RNG state replayed per frame index so that the result does not depend
-    on the sharding). With torch.distributed initialised (or rank/world given) each rank processes its frame range and,
-    if `gather`, the states are all-gathered so that every rank returns the whole video. `pipeline`: an existing
-    DetectPipeline to reuse (anything with its detect_stream / eng interface)."""
+    on the sharding or on the order in which batches are decoded). With torch.distributed initialised (or rank/world
+    given) each rank processes its frame range and, if `gather` and a process group exists, the states are all-gathered
+    so that every rank returns the whole video; a file shorter than its header claims simply yields fewer frames.
+    `pipeline`: an existing DetectPipeline to reuse (anything with its detect_stream / eng interface). `decoders`: decoder
+    threads of this rank, each with `depth` pinned batch buffers (page-locking memory is slow: keep batch x depth x
+    decoders modest, e.g. 16 x 3 x 8 frames of 1080p = 2.4 GB) (file sources; the streaming mode "full" needs frame order and uses one). `stats`, if given,
+    receives {"frames": frames this rank processed, "range": (start, stop)}."""
     import collections
     import torch.distributed as dist
     from .engine import rng_seed, rng_advance
+    have_group = dist.is_available() and dist.is_initialized()
     if rank is None or world is None:
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(), dist.get_world_size()
-        else:
-            rank, world = 0, 1
-    _, n_total, H, W = open_source(source)
+        rank, world = (dist.get_rank(), dist.get_world_size()) if have_group else (0, 1)
+    n_total, H, W = probe(source)
+    if have_group and world > 1:       # every rank must shard the same count: rank 0's view of the file wins
+        obj = [n_total]
+        dist.broadcast_object_list(obj, src=0)
+        n_total = int(obj[0])
     start, stop = sharding.shard_range(n_total, rank, world)
-    src = FrameSource(source, start, stop, batch=batch, depth=5)
+    src = FrameSource(source, start, stop, batch=batch, depth=depth, decoders=1 if mode == "full" else decoders)
     pipe = pipeline or DetectPipeline(H, W, gsize, mode=mode, sub_batch=min(16, batch), cnn_params=cnn_params, engine=engine)
     st0 = rng_seed(0) if rng_state is None else rng_state
     inflight = collections.deque()
 
     def batches():
         for buf, m, pos in src:
-            inflight.append(buf)
+            inflight.append((buf, m, pos))
             yield buf[:m], mtx, rng_advance(st0, pos)
 
-    parts = {}
-    for res in pipe.detect_stream(batches(), depth=2):
-        for k, v in res.items():
-            parts.setdefault(k, []).append(v.copy())
-        src.release(inflight.popleft())             # results are ready, so this batch's uploads have completed
     names = {"neural": ("stones", "keep", "conf"), "clustering": ("km_stones", "km_trusted"),
-             "both": ("stones", "keep", "conf", "km_stones", "km_trusted")}[mode]
-    out = {}
-    for k in names:
-        if k in parts:
-            out[k] = np.concatenate(parts[k])
-        else:
-            shape = (0,) if k == "km_trusted" else (0, gsize, gsize)
-            out[k] = np.zeros(shape, np.float32 if k == "conf" else np.uint8)
-    if gather and world > 1:
+             "both": ("stones", "keep", "conf", "km_stones", "km_trusted"),
+             "full": ("stones", "keep", "conf", "km_stones", "km_trusted", "fg_counts")}[mode]
+    shapes = {"km_trusted": (), "fg_counts": (gsize, gsize)}
+    dtypes = {"conf": np.float32, "fg_counts": np.int32}
+    out = {k: np.zeros((max(0, stop - start),) + shapes.get(k, (gsize, gsize)), dtypes.get(k, np.uint8)) for k in names}
+    done = 0
+    for res in pipe.detect_stream(batches(), depth=2):
+        buf, m, pos = inflight.popleft()
+        for k in names:
+            out[k][pos - start:pos - start + m] = res[k]
+        done = max(done, pos - start + m)
+        src.release(buf)                            # results are ready, so this batch's uploads have completed
+    for k in names:                                 # a short file: keep what was really read
+        out[k] = out[k][:done]
+    if stats is not None:
+        stats.update(frames=done, range=(start, stop))
+    if gather and world > 1 and have_group:
         dev = pipe.eng.device if dist.get_backend() == "nccl" else torch.device("cpu")   # gloo gathers on the host
         for k in names:
-            out[k] = sharding.gather_board_states(torch.from_numpy(out[k]).to(dev), n_total).cpu().numpy()
+            out[k] = sharding.gather_ragged(torch.from_numpy(out[k]).to(dev)).cpu().numpy()
     return out

@@ -13,7 +13,9 @@
  *   - the caller owns every device buffer (raw device pointers) and the CUDA stream (cudaStream_t passed as void*);
  *     the library owns only the opaque context (constant tables, packed CNN weights);
  *   - all work is enqueued on `stream` and is asynchronous with respect to the host; no function synchronises;
- *   - one context per finder instance / thread; contexts share no mutable state;
+ *   - one context per finder instance / thread; contexts share no mutable state. Every kernel-launching entry point
+ *     makes the context's device current on the calling thread (cudaSetDevice) and leaves it current: a thread that
+ *     drives contexts on several GPUs must not rely on the current device across calls;
  *   - images are BGR uint8, interleaved, row-major (what cv2.VideoCapture hands the reference, vmanager.py:584);
  *   - board colours are uint8 codes CKB_E / CKB_B / CKB_W (the reference's Golib constants 'E','B','W').
  */
@@ -58,6 +60,12 @@ const char *ckb_last_error(const ckb_ctx *ctx);
 #define CKB_RNG_DRAWS_PER_KMEANS 39
 uint64_t ckb_rng_seed(uint32_t seed);
 uint64_t ckb_rng_advance(uint64_t state, uint64_t n_draws);
+
+/* Geometry tables of the canonical image (host helpers; the kernels hold the same tables on the device).
+ * Replaces: StonesFinder.getrect(r, c)  stonesfinder.py:412-450  -> rects4: gsize*gsize x {x0, y0, x1, y1}, row-major (x = row)
+ *           StonesFinder.getmask()      stonesfinder.py:452-493  -> mask: (20 gsize)^2 uint8, 1 inside each zone's disk */
+int ckb_zone_rects(int gsize, int32_t *rects4);
+int ckb_zone_mask(int gsize, uint8_t *mask);
 
 /* 3x3 inverse exactly as cv::invert computes it for the matrix warpPerspective receives (host helper). */
 int ckb_invert_homography(const double *m9, double *minv9);

@@ -57,3 +57,32 @@ def test_frame_source_array_and_errors(clip):
     assert np.array_equal(np.concatenate(out), frames[3:11])
     with pytest.raises(IOError):
         open_source(os.path.join(os.path.dirname(__file__), "no_such_video.avi"))
+
+
+def test_frame_source_several_decoders_cover_the_range(clip):
+    """decoders = 3: three captures over contiguous parts of the range; batches arrive interleaved, each tagged with its
+    first frame index, every frame exactly once and bit-exact."""
+    from camkifu_b200.video import FrameSource
+    path, frames, _ = clip
+    src = FrameSource(path, 2, 23, batch=4, depth=2, decoders=3)
+    seen = np.zeros(23, bool)
+    for buf, m, first in src:
+        assert np.array_equal(buf[:m].numpy(), frames[first:first + m])
+        assert not seen[first:first + m].any()
+        seen[first:first + m] = True
+        src.release(buf)
+    assert seen[2:].all() and not seen[:2].any() and src.frames_read == 21
+
+
+def test_ring_clip_is_zero_copy():
+    import torch
+    from camkifu_b200.video import FrameSource, RingClip
+    ring = torch.arange(5 * 4 * 6 * 3, dtype=torch.uint8).reshape(5, 4, 6, 3)
+    src = FrameSource(RingClip(ring, 23), 3, 23, batch=4)
+    pos = 3
+    for buf, m, first in src:
+        assert first == pos and buf.data_ptr() == ring[first % 5].data_ptr()      # a view of the ring, not a copy
+        assert torch.equal(buf[:m], ring[first % 5:first % 5 + m])
+        pos += m
+        src.release(buf)
+    assert pos == 23
