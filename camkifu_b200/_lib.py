@@ -35,6 +35,11 @@ SIGNATURES = {
     "ckb_find_stones_workspace": (C.c_size_t, [C.c_void_p, C.c_int]),
     "ckb_find_stones": (C.c_int, [C.c_void_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _vp,
                                   C.c_size_t, _u8p, _u8p, _u8p, _f32p, _f64p, _i32p, C.c_void_p]),
+    "ckb_find_stones_regions_workspace": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ckb_find_stones_regions": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _i32p, _u64p, _vp, C.c_size_t, _u8p, _u8p, _u8p,
+                                          _f32p, _f64p, C.c_void_p]),
+    "ckb_zone_means": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_void_p]),
+    "ckb_history_vote": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, _u8p, C.c_void_p]),
     "ckb_set_cnn_weights": (C.c_int, [C.c_void_p, _f32p, C.c_size_t]),
     "ckb_cnn_workspace": (C.c_size_t, [C.c_void_p, C.c_int]),
     "ckb_cnn_forward": (C.c_int, [C.c_void_p, _u8p, C.c_int, _vp, C.c_size_t, _f32p, _u8p, _f32p, _u8p, C.c_void_p]),

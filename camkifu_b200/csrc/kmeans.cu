@@ -41,12 +41,13 @@
 template <bool F32>
 __global__ void __launch_bounds__(256) ckb_pack_region(const void *__restrict__ imgs, int S, Region rg,
                                                        void *__restrict__ scratch, size_t scratch_stride,
-                                                       const KmAttempt *__restrict__ only_flagged)
+                                                       const KmAttempt *__restrict__ only_flagged, int nreg, int reg)
 {
     const int f = blockIdx.y;
     // uint8 path: only the frames with an attempt the cluster kernel declined are packed (normally none)
-    if (only_flagged && only_flagged[f * 3].iters != KM_ITERS_FALLBACK && only_flagged[f * 3 + 1].iters != KM_ITERS_FALLBACK &&
-        only_flagged[f * 3 + 2].iters != KM_ITERS_FALLBACK)
+    const int u3 = (f * nreg + reg) * 3;
+    if (only_flagged && only_flagged[u3].iters != KM_ITERS_FALLBACK && only_flagged[u3 + 1].iters != KM_ITERS_FALLBACK &&
+        only_flagged[u3 + 2].iters != KM_ITERS_FALLBACK)
         return;
     char *dst = (char *)scratch + (size_t)f * scratch_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rg.N; i += gridDim.x * blockDim.x) {
@@ -238,11 +239,14 @@ template <bool F32, int NT>
 __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict__ scratch,
                                                                  size_t scratch_stride, int N,
                                                                  const uint64_t *__restrict__ rng_states,
-                                                                 KmAttempt *__restrict__ results, int only_flagged)
+                                                                 KmAttempt *__restrict__ results, int only_flagged,
+                                                                 int nreg, int reg)
 {
     constexpr int NW = NT / 32;
+    // batched multi-region calls: rng_states / results are indexed by unit = frame * nreg + region (scratch by frame)
+    const int unit = blockIdx.y * nreg + reg;
     // uint8 path: this kernel is the fallback of ckb_kmeans_cluster_u8 and runs only the attempts that one declined
-    if (only_flagged && results[blockIdx.y * 3 + blockIdx.x].iters != KM_ITERS_FALLBACK) return;
+    if (only_flagged && results[unit * 3 + blockIdx.x].iters != KM_ITERS_FALLBACK) return;
     // uint8 input: the labels of the current iteration are kept (1 byte per pixel, behind the packed pixels in this
     // frame's scratch slot, one array per attempt) so that the compactness pass need not recompute the three distances
     // (7 N bytes of the 16 S^2-byte slot; the pixel part is only ever read, the label part only by this CTA)
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
     const int nseg = (N + KM_SEG - 1) / KM_SEG;
 
     // ---- cv::RNG draws of this attempt: 1 integer + 6 doubles = 13 draws
-    uint64_t st = rng_states[frame];
+    uint64_t st = rng_states[unit];
     for (int k = 0; k < 13 * attempt; k++) rng_next(st);
     const int c0 = (int)(rng_next(st) % (uint32_t)N);
     double u[6];
@@ -650,7 +654,7 @@ __global__ void __launch_bounds__(NT) ckb_kmeans_attempt(const void *__restrict_
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < NW; w++) t += sh.red_d[w];
-            KmAttempt &r = results[frame * 3 + attempt];
+            KmAttempt &r = results[unit * 3 + attempt];
             r.compactness = t;
             for (int k = 0; k < 9; k++) { r.centers[k] = sh.cen[k]; r.old_centers[k] = sh.oldc[k]; }
             r.n_fix = sh.n_fix;
@@ -697,7 +701,7 @@ __device__ __forceinline__ float3 zc_pixel(const void *base, int S, const Region
 // `tickets`, which the launcher zeroes) runs check_density over the frame's 361 stones.
 template <bool F32>
 __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__restrict__ pixels, size_t frame_stride,
-                                                                Region rg, int gsize, int rs, int re, int cs, int ce,
+                                                                const __grid_constant__ RegionSet regs, int gsize,
                                                                 const KmAttempt *__restrict__ results,
                                                                 const int32_t *__restrict__ rects,
                                                                 const uint8_t *__restrict__ mask, int S,
@@ -711,9 +715,13 @@ __global__ void __launch_bounds__(ZC_THREADS) ckb_zone_classify(const void *__re
 {
     __shared__ int s_hist[3];
     __shared__ int s_last;
-    const int frame = blockIdx.y;
+    // one unit per (frame, region); every output is indexed by unit (= frame for the single-region calls)
+    const int unit = blockIdx.y, fr = unit / regs.n;
+    const Region rg = regs.r[unit - fr * regs.n];
+    const int rs = rg.rs, re = rg.re, cs = rg.cs, ce = rg.ce;
+    const int frame = unit;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const void *px = (const char *)pixels + (size_t)frame * frame_stride;
+    const void *px = (const char *)pixels + (size_t)fr * frame_stride;
 
     // best attempt: `if (compactness < best_compactness)` in attempt order, starting from DBL_MAX
     int best = 0;
@@ -827,22 +835,86 @@ static Region make_region(const ckb_ctx *ctx, int rs, int re, int cs, int ce)
     r.h = ctx->h_rects[((re - 1) * g + (ce - 1)) * 4 + 2] - r.x0;
     r.w = ctx->h_rects[((re - 1) * g + (ce - 1)) * 4 + 3] - r.y0;
     r.N = r.h * r.w;
+    r.rs = rs; r.re = re; r.cs = cs; r.ce = ce;
     return r;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const Region &rg, const uint64_t *d_rng_states,
+int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const RegionSet &regs, const uint64_t *d_rng_states,
                               KmAttempt *d_results, cudaStream_t st);
 
-// workspace: [n] per-frame scratch (packed pixels + label caches of the one-CTA kernel) | [3 n] KmAttempt | [n][361]
-// stones of the zone vote | [n] tickets
+// workspace: [n] per-frame scratch (packed pixels + label caches of the one-CTA kernel) | [3 units] KmAttempt |
+// [units][361] stones of the zone vote | [units] tickets          (units = n frames x n_regions)
+static size_t find_stones_workspace(const ckb_ctx *ctx, int n, int nreg)
+{
+    const size_t per_frame = align_up((size_t)ctx->S * ctx->S * 16, 256);
+    const size_t units = (size_t)n * nreg;
+    return (size_t)n * per_frame + align_up(units * 3 * sizeof(KmAttempt), 256) + align_up(units * CKB_MAX_ZONES, 256) +
+           align_up(units * sizeof(unsigned), 256) + 256;
+}
+
 extern "C" size_t ckb_find_stones_workspace(const ckb_ctx *ctx, int n)
 {
     if (!ctx || n < 0) return 0;
-    const size_t per_frame = align_up((size_t)ctx->S * ctx->S * 16, 256);
-    return (size_t)n * per_frame + align_up((size_t)n * 3 * sizeof(KmAttempt), 256) +
-           align_up((size_t)n * CKB_MAX_ZONES, 256) + align_up((size_t)n * sizeof(unsigned), 256) + 256;
+    return find_stones_workspace(ctx, n, 1);
+}
+
+extern "C" size_t ckb_find_stones_regions_workspace(const ckb_ctx *ctx, int n, int n_regions)
+{
+    if (!ctx || n < 0 || n_regions < 1 || n_regions > CKB_MAX_REGIONS) return 0;
+    return find_stones_workspace(ctx, n, n_regions);
+}
+
+static int find_stones_impl(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, const RegionSet &regs,
+                            const uint64_t *d_rng_states, void *d_work, size_t work_bytes, uint8_t *d_stones,
+                            uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness,
+                            int32_t *d_labels, void *stream)
+{
+    const int g = ctx->gsize, nreg = regs.n;
+    if (work_bytes < find_stones_workspace(ctx, n, nreg)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_find_stones: workspace too small");
+    if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: workspace must be 256-byte aligned");
+    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CKB_ENTER(ctx, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t stride = align_up((size_t)ctx->S * ctx->S * 16, 256);
+    const size_t units = (size_t)n * nreg;
+    char *w = (char *)d_work + (size_t)n * stride;
+    KmAttempt *res = (KmAttempt *)w;
+    w += align_up(units * 3 * sizeof(KmAttempt), 256);
+    uint8_t *stones_ws = (uint8_t *)w;
+    w += align_up(units * CKB_MAX_ZONES, 256);
+    unsigned *tickets = (unsigned *)w;
+    CKB_CUDA(ctx, cudaMemsetAsync(tickets, 0, units * sizeof(unsigned), st));
+    if (is_f32) {
+        const Region &rg = regs.r[0];          // float32 images: single-region calls only
+        dim3 pgrid((rg.N + 255) / 256, n);
+        ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride, nullptr, 1, 0);
+        CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
+        ckb_kmeans_attempt<true, KM_THREADS_F32><<<dim3(3, n), KM_THREADS_F32, 0, st>>>(d_work, stride, rg.N, d_rng_states, res, 0, 1, 0);
+        CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
+        ckb_zone_classify<true><<<dim3(ZC_SPLIT, n), ZC_THREADS, 0, st>>>(d_work, stride, regs, g, res, ctx->d_rects, ctx->d_mask,
+                                                                         ctx->S, stones_ws, tickets, d_stones, d_trusted,
+                                                                         d_ratios, d_centers, d_compactness, d_labels);
+        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
+    } else {
+        // uint8 images: one thread-block cluster per (frame, region), pixels resident in distributed shared memory, the
+        // three attempts in lock step (kmeans_cluster.cu). The attempts it declines (an empty cluster; sums within reach
+        // of 2^25: pathological images) are marked in `res` and re-run by the one-CTA kernel, which otherwise exits at once.
+        const int rc = ckb_launch_kmeans_cluster(ctx, (const uint8_t *)d_imgs, n, regs, d_rng_states, res, st);
+        if (rc != CKB_OK) return rc;
+        for (int r = 0; r < nreg; r++) {
+            ckb_pack_region<false><<<dim3(8, n), 256, 0, st>>>(d_imgs, ctx->S, regs.r[r], d_work, stride, res, nreg, r);
+            CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
+            ckb_kmeans_attempt<false, 1024><<<dim3(3, n), 1024, 0, st>>>(d_work, stride, regs.r[r].N, d_rng_states, res, 1, nreg, r);
+            CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
+        }
+        ckb_zone_classify<false><<<dim3(ZC_SPLIT, (unsigned)units), ZC_THREADS, 0, st>>>(
+            d_imgs, (size_t)ctx->S * ctx->S * 3, regs, g, res, ctx->d_rects, ctx->d_mask, ctx->S, stones_ws, tickets, d_stones,
+            d_trusted, d_ratios, d_centers, d_compactness, d_labels);
+        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
+    }
+    return CKB_OK;
 }
 
 extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, int rs, int re, int cs, int ce,
@@ -856,45 +928,34 @@ extern "C" int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int
     if (!d_imgs || !d_rng_states || !d_work || n < 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: bad argument");
     if (rs < 0 || cs < 0 || re > g || ce > g || rs >= re || cs >= ce)
         CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: region [%d,%d)x[%d,%d) outside the %dx%d goban", rs, re, cs, ce, g, g);
-    if (work_bytes < ckb_find_stones_workspace(ctx, n)) CKB_FAIL(ctx, CKB_E_NOMEM, "ckb_find_stones: workspace too small");
-    if (((uintptr_t)d_work & 255) != 0) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: workspace must be 256-byte aligned");
-    CKB_CUDA(ctx, cudaSetDevice(ctx->device));
-    CKB_ENTER(ctx, stream);
-    cudaStream_t st = (cudaStream_t)stream;
-    const Region rg = make_region(ctx, rs, re, cs, ce);
-    const size_t stride = align_up((size_t)ctx->S * ctx->S * 16, 256);
-    char *w = (char *)d_work + (size_t)n * stride;
-    KmAttempt *res = (KmAttempt *)w;
-    w += align_up((size_t)n * 3 * sizeof(KmAttempt), 256);
-    uint8_t *stones_ws = (uint8_t *)w;
-    w += align_up((size_t)n * CKB_MAX_ZONES, 256);
-    unsigned *tickets = (unsigned *)w;
-    CKB_CUDA(ctx, cudaMemsetAsync(tickets, 0, (size_t)n * sizeof(unsigned), st));
-    dim3 pgrid((rg.N + 255) / 256, n);
-    if (is_f32) {
-        ckb_pack_region<true><<<pgrid, 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride, nullptr);
-        CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        ckb_kmeans_attempt<true, KM_THREADS_F32><<<dim3(3, n), KM_THREADS_F32, 0, st>>>(d_work, stride, rg.N, d_rng_states, res, 0);
-        CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
-        ckb_zone_classify<true><<<dim3(ZC_SPLIT, n), ZC_THREADS, 0, st>>>(d_work, stride, rg, g, rs, re, cs, ce, res, ctx->d_rects,
-                                                                         ctx->d_mask, ctx->S, stones_ws, tickets, d_stones,
-                                                                         d_trusted, d_ratios, d_centers, d_compactness, d_labels);
-        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
-    } else {
-        // uint8 images: one thread-block cluster per (frame, attempt), pixels resident in distributed shared memory
-        // (kmeans_cluster.cu). The attempts it declines (an empty cluster; sums within reach of 2^25: pathological
-        // images) are marked in `res` and re-run by the one-CTA kernel, which otherwise exits at once.
-        const int rc = ckb_launch_kmeans_cluster(ctx, (const uint8_t *)d_imgs, n, rg, d_rng_states, res, st);
-        if (rc != CKB_OK) return rc;
-        ckb_pack_region<false><<<dim3(8, n), 256, 0, st>>>(d_imgs, ctx->S, rg, d_work, stride, res);   // exits at once unless flagged
-        CKB_LAUNCH_CHECK(ctx, "ckb_pack_region");
-        ckb_kmeans_attempt<false, 1024><<<dim3(3, n), 1024, 0, st>>>(d_work, stride, rg.N, d_rng_states, res, 1);
-        CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_attempt");
-        ckb_zone_classify<false><<<dim3(ZC_SPLIT, n), ZC_THREADS, 0, st>>>(d_imgs, (size_t)ctx->S * ctx->S * 3, rg, g, rs, re, cs, ce,
-                                                                          res, ctx->d_rects, ctx->d_mask, ctx->S, stones_ws,
-                                                                          tickets, d_stones, d_trusted, d_ratios, d_centers,
-                                                                          d_compactness, d_labels);
-        CKB_LAUNCH_CHECK(ctx, "ckb_zone_classify");
+    RegionSet regs;
+    memset(&regs, 0, sizeof regs);
+    regs.n = 1;
+    regs.r[0] = make_region(ctx, rs, re, cs, ce);
+    return find_stones_impl(ctx, d_imgs, is_f32, n, regs, d_rng_states, d_work, work_bytes, d_stones, d_trusted, d_ratios,
+                            d_centers, d_compactness, d_labels, stream);
+}
+
+extern "C" int ckb_find_stones_regions(ckb_ctx *ctx, const uint8_t *d_imgs, int n, int n_regions, const int *h_regions4,
+                                       const uint64_t *d_rng_states, void *d_work, size_t work_bytes, uint8_t *d_stones,
+                                       uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness,
+                                       void *stream)
+{
+    if (!ctx) return CKB_E_INVALID;
+    const int g = ctx->gsize;
+    if (n == 0) return CKB_OK;
+    if (!d_imgs || !d_rng_states || !d_work || !h_regions4 || n < 0 || n_regions < 1 || n_regions > CKB_MAX_REGIONS)
+        CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones_regions: bad argument (1 .. %d regions)", CKB_MAX_REGIONS);
+    RegionSet regs;
+    memset(&regs, 0, sizeof regs);
+    regs.n = n_regions;
+    for (int r = 0; r < n_regions; r++) {
+        const int rs = h_regions4[4 * r], re = h_regions4[4 * r + 1], cs = h_regions4[4 * r + 2], ce = h_regions4[4 * r + 3];
+        if (rs < 0 || cs < 0 || re > g || ce > g || rs >= re || cs >= ce)
+            CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones_regions: region %d [%d,%d)x[%d,%d) outside the %dx%d goban", r, rs,
+                     re, cs, ce, g, g);
+        regs.r[r] = make_region(ctx, rs, re, cs, ce);
     }
-    return CKB_OK;
+    return find_stones_impl(ctx, d_imgs, 0, n, regs, d_rng_states, d_work, work_bytes, d_stones, d_trusted, d_ratios, d_centers,
+                            d_compactness, nullptr, stream);
 }

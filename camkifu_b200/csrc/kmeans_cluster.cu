@@ -339,7 +339,8 @@ __device__ __forceinline__ void pp_sample_cluster(cg::cluster_group &cluster, Kc
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uint8_t *__restrict__ imgs, int S, Region rg, int cpc,
+__global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uint8_t *__restrict__ imgs, int S,
+                                                                      const __grid_constant__ RegionSet regs, int cpc,
                                                                       const uint64_t *__restrict__ rng_states,
                                                                       KmAttempt *__restrict__ results)
 {
@@ -347,7 +348,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     const size_t img_bytes = (size_t)S * S * 3;     // the vector loads never read past the frame they belong to
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const int frame = blockIdx.x / C;
+    // one cluster per (frame, region): rng_states[unit], results[3 unit + attempt]
+    const int unit = blockIdx.x / C, frame = unit / regs.n;
+    const Region rg = regs.r[unit - frame * regs.n];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // the serial steps (totals, sampling, centre update) run on the highest-numbered warps: the warp scheduler favours
     // them, and they are the critical path of every CTA that waits at the next barrier
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     const bool vec_ok = (((uintptr_t)imgs) & 3) == 0;
     if (tid < 3) {
         // cv::RNG draws of attempt `tid`: 1 integer + 6 doubles = 13 draws per attempt
-        uint64_t st = rng_states[frame];
+        uint64_t st = rng_states[unit];
         for (int k = 0; k < 13 * tid; k++) rng_next(st);
         const int c0 = (int)(rng_next(st) % (uint32_t)N);
         for (int k = 0; k < 6; k++) sh.u[tid][k] = rng_double(st);
@@ -819,7 +822,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     cluster.sync();
     if (rank == 0 && tid < 3) {
         const int a = tid;
-        KmAttempt &res = results[frame * 3 + a];
+        KmAttempt &res = results[unit * 3 + a];
         if (sh.state[a] == 1) {
             double t = 0.0;
             for (int r = 0; r < C; r++) t += sh.xcomp[r][a];
@@ -834,7 +837,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     }
     KC_TICK(8);   // compactness
 #ifdef KC_TIMING
-    if (tid == 0 && frame == (gridDim.x / C > 50 ? 50 : 0))
+    if (tid == 0 && unit == (gridDim.x / C > 50 ? 50 : 0))
         printf("rank %d iters %d %d %d: load %lld  sync0 %lld  pp %lld  pass %lld  wait %lld  xchg %lld  tail %lld (search %lld sweep %lld wait %lld)  centres %lld  compact %lld  total %lld\n",
                rank, sh.iters[0], sh.iters[1], sh.iters[2], tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[9], tk[10], tk[11], tk[7], tk[8], clock64() - t_begin);
 #endif
@@ -854,12 +857,15 @@ static int kc_cluster_size(int N)
 
 #define KC_BYTES_PER_CHUNK (KC_CH * 4 + 3 * 16 + 8 + 12 * 4 + 4)
 
-int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const Region &rg, const uint64_t *d_rng_states,
+// n frames x regs.n regions: one cluster per (frame, region); d_rng_states / d_results are indexed by frame * regs.n + region
+int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const RegionSet &regs, const uint64_t *d_rng_states,
                               KmAttempt *d_results, cudaStream_t st)
 {
     constexpr int NT = 512;
-    const int C = kc_cluster_size(rg.N);
-    const int nchunk = (rg.N + KC_CH - 1) / KC_CH;
+    int maxN = 1;
+    for (int i = 0; i < regs.n; i++) maxN = regs.r[i].N > maxN ? regs.r[i].N : maxN;
+    const int C = kc_cluster_size(maxN);                 // sized for the largest region of the call
+    const int nchunk = (maxN + KC_CH - 1) / KC_CH;
     const int cpc = (nchunk + C - 1) / C;
     if (cpc > 141) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_find_stones: region too large for a cluster of %d", C);
     const size_t dyn = (size_t)cpc * KC_BYTES_PER_CHUNK;
@@ -870,7 +876,7 @@ int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const 
         attr_set[ctx->device] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n * C), 1, 1);
+    cfg.gridDim = dim3((unsigned)(n * regs.n * C), 1, 1);
     cfg.blockDim = dim3(NT, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = st;
@@ -882,7 +888,7 @@ int ckb_launch_kmeans_cluster(ckb_ctx *ctx, const uint8_t *d_imgs, int n, const 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int S = ctx->S;
-    CKB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ckb_kmeans_cluster_u8<NT>, d_imgs, S, rg, cpc, d_rng_states, d_results));
+    CKB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ckb_kmeans_cluster_u8<NT>, d_imgs, S, regs, cpc, d_rng_states, d_results));
     CKB_LAUNCH_CHECK(ctx, "ckb_kmeans_cluster");
     return CKB_OK;
 }

@@ -20,7 +20,14 @@ struct KmAttempt {
 };
 
 struct Region {
-    int x0, y0, h, w, N;
+    int x0, y0, h, w, N;   // bounding box of the zones [rs, re) x [cs, ce) in the canonical image (cluster_colors' sub-image)
+    int rs, re, cs, ce;
+};
+
+#define CKB_MAX_REGIONS 16
+struct RegionSet {         // the regions of one batched call (SfMeta: 3 x 3), passed to the kernels by value
+    Region r[CKB_MAX_REGIONS];
+    int n;
 };
 
 // ----------------------------------------------------------------------------------------------------------- helpers

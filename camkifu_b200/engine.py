@@ -216,6 +216,69 @@ class StoneEngine:
                                            self._ptr(out.get("labels")), self._stream()))
         return out
 
+    def find_stones_regions(self, imgs: torch.Tensor, regions, rng_states, want=("stones", "trusted")):
+        """SfClustering.find_stones(img, rs, re, cs, ce) for every region of `regions` ([(rs, re, cs, ce)], at most 16) on
+        each of the n uint8 canonical images, in one set of launches (SfMeta's 3 x 3 Regions, sf_meta.py:245-262).
+        rng_states: [n][n_regions] cv::RNG states (ints) or a CUDA int64 tensor of that shape. Returns device tensors
+        indexed [image, region]: stones [n, R, g, g] (E outside each region), trusted [n, R], ..."""
+        g = self.gsize
+        if imgs.dim() == 3:
+            imgs = imgs.unsqueeze(0)
+        assert imgs.is_contiguous() and imgs.dtype == torch.uint8 and imgs.shape[1:] == (self.S, self.S, 3)
+        n, R = imgs.shape[0], len(regions)
+        reg = np.ascontiguousarray(np.asarray(regions, dtype=np.int32).reshape(R, 4))
+        if isinstance(rng_states, torch.Tensor):
+            st = rng_states
+            assert st.is_cuda and st.dtype == torch.int64 and st.is_contiguous()
+        else:
+            st = torch.as_tensor(np.asarray(rng_states, dtype=np.uint64).astype(np.int64), device=self.device)
+        assert st.numel() == n * R
+        dev = self.device
+        out = {"stones": torch.empty((n, R, g, g), dtype=torch.uint8, device=dev),
+               "trusted": torch.empty((n, R), dtype=torch.uint8, device=dev)}
+        if "ratios" in want:
+            out["ratios"] = torch.empty((n, R, g, g, 3), dtype=torch.uint8, device=dev)
+        if "centers" in want:
+            out["centers"] = torch.empty((n, R, 3, 3), dtype=torch.float32, device=dev)
+        if "compactness" in want:
+            out["compactness"] = torch.empty((n, R), dtype=torch.float64, device=dev)
+        wb = self.L.ckb_find_stones_regions_workspace(self._h, n, R)
+        work = self._workspace(wb, "kmeans")
+        self._check(self.L.ckb_find_stones_regions(self._h, self._ptr(imgs), n, R, reg.ctypes.data_as(C.c_void_p),
+                                                   self._ptr(st), self._ptr(work), work.numel(), self._ptr(out["stones"]),
+                                                   self._ptr(out["trusted"]), self._ptr(out.get("ratios")),
+                                                   self._ptr(out.get("centers")), self._ptr(out.get("compactness")),
+                                                   self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------ SfMeta / SfContours statistics
+    def zone_means(self, imgs: torch.Tensor, masks: torch.Tensor, rs=0, re=None, cs=0, ce=None) -> torch.Tensor:
+        """The zone table of SfContours.find_stones (sf_contours.py:87-102,113-126): int16 [n, re-rs, ce-cs, 4] = visible
+        flag + mean B, G, R. masks: uint8 [n, S, S], non-zero under the filled convex hulls (built on the host)."""
+        g = self.gsize
+        re = g if re is None else re
+        ce = g if ce is None else ce
+        if imgs.dim() == 3:
+            imgs, masks = imgs.unsqueeze(0), masks.unsqueeze(0)
+        n = imgs.shape[0]
+        assert imgs.is_contiguous() and imgs.dtype == torch.uint8 and imgs.shape[1:] == (self.S, self.S, 3)
+        assert masks.is_contiguous() and masks.dtype == torch.uint8 and masks.shape == (n, self.S, self.S)
+        out = torch.empty((n, re - rs, ce - cs, 4), dtype=torch.int16, device=self.device)
+        self._check(self.L.ckb_zone_means(self._h, self._ptr(imgs), self._ptr(masks), n, rs, re, cs, ce, self._ptr(out),
+                                          self._stream()))
+        return out
+
+    def history_vote(self, history: torch.Tensor, is_empty: torch.Tensor) -> torch.Tensor:
+        """Region.commit's vote (sf_meta.py:305-340). history: uint8 [..., histo] colour codes, is_empty: uint8 [...]
+        (both on the device). Returns uint8 [...]: 0 = nothing to submit, 1 = B, 2 = W."""
+        assert history.is_cuda and history.dtype == torch.uint8 and history.is_contiguous()
+        assert is_empty.is_cuda and is_empty.dtype == torch.uint8 and is_empty.is_contiguous()
+        assert tuple(history.shape[:-1]) == tuple(is_empty.shape)
+        out = torch.empty_like(is_empty)
+        self._check(self.L.ckb_history_vote(self._h, self._ptr(history), self._ptr(is_empty), is_empty.numel(),
+                                            history.shape[-1], self._ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------------------------------------------------------------------ K4
     def set_cnn_weights(self, params: np.ndarray):
         p = np.ascontiguousarray(params, dtype=np.float32).ravel()

@@ -123,6 +123,30 @@ int ckb_find_stones(ckb_ctx *ctx, const void *d_imgs, int is_f32, int n, int rs,
                     uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness, int32_t *d_labels,
                     void *stream);
 
+/* Batched form for SfMeta, whose 3 x 3 Regions each call cluster.find_stones(img, rs=, re=, cs=, ce=) on the same image
+ * (sf_meta.py:245-262 try_clustering, :232-243 routine): n_regions (<= 16) regions x n uint8 images in one set of launches.
+ * h_regions4: n_regions x {rs, re, cs, ce} (HOST). d_rng_states: n x n_regions states (image-major), the state of the
+ * call (image, region). Outputs are indexed the same way: d_stones n x n_regions x g*g (E outside each region), d_trusted
+ * n x n_regions, d_ratios n x n_regions x g*g*3, d_centers n x n_regions x 9, d_compactness n x n_regions. */
+size_t ckb_find_stones_regions_workspace(const ckb_ctx *ctx, int n, int n_regions);
+int ckb_find_stones_regions(ckb_ctx *ctx, const uint8_t *d_imgs, int n, int n_regions, const int *h_regions4,
+                            const uint64_t *d_rng_states, void *d_work, size_t work_bytes, uint8_t *d_stones,
+                            uint8_t *d_trusted, uint8_t *d_ratios, float *d_centers, double *d_compactness, void *stream);
+
+/* ---- per-zone statistics of SfMeta / SfContours ------------------------------------------------------
+ * ckb_zone_means replaces the zone loop of SfContours.find_stones and _norm_channels   sf_contours.py:87-102,113-126
+ *   d_imgs n canonical images; d_masks n x S x S uint8, non-zero where the reference's `mask` (filled convex hulls of the
+ *   contours, drawn on the host: Canny / findContours / convexHull stay on the CPU) is 1, in canonical image coordinates.
+ *   d_zones n x (re-rs) x (ce-cs) x 4 int16: [0] = 1 if more than 40 % of the zone's pixels are under the mask, [1..3] =
+ *   int16(sum of the B, G, R values of the visible pixels / their number) if so, else the same over the masked-out pixels.
+ * ckb_history_vote replaces the per-intersection vote of Region.commit                  sf_meta.py:305-340
+ *   d_history n_items x histo uint8 colour codes (the CyclicBuffer entries of an intersection, any order), d_is_empty
+ *   n_items uint8 (StonesFinder.is_empty); d_moves n_items uint8: 0 = nothing to submit, CKB_B / CKB_W = the move. */
+int ckb_zone_means(ckb_ctx *ctx, const uint8_t *d_imgs, const uint8_t *d_masks, int n, int rs, int re, int cs, int ce,
+                   int16_t *d_zones, void *stream);
+int ckb_history_vote(ckb_ctx *ctx, const uint8_t *d_history, const uint8_t *d_is_empty, int n_items, int histo,
+                     uint8_t *d_moves, void *stream);
+
 /* ---- K4 -----------------------------------------------------------------------------------------------------------
  * Replaces: NNManager.get_net() / create_net() weights                              nn_manager.py:58-74,277-298
  * h_params: CKB_CNN_NPARAM float32 in Keras channels-last order (w1 b1 w2 b2 w3 b3 w4 b4 w5 b5 w6 b6, conv kernels

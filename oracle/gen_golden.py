@@ -17,6 +17,9 @@ The reference cannot travel to the GPU box, so its outputs on seeded synthetic i
                            clip (a hand places two stones): the MOG2 foreground masks of _learn_bg
                            (stonesfinder.py:113-115,171-176) and the per-zone foreground sums is_agitated reduces them to
                            (sf_neural.py:178-180)
+  meta.npz                 SfMeta / SfContours per-zone statistics: the zone table of the unmodified
+                           SfContours.find_stones with the mask it was computed from, Region.commit's votes on random
+                           histories, Region.check_foreground of the 3 x 3 regions on random masks (see gen_meta)
   neural_stream.npz        the unmodified SfNeural._find over 72 frames of such a clip (background sampling, initial
                            assessment, mark_targets / select_targets / process_targets / lookback, sf_neural.py:36-176)
                            with `net.predict` = the oracle's float32 forward on the trained fixture weights
@@ -218,6 +221,146 @@ def gen_background():
     print("background: fg pixels per frame", [int(z.sum()) for z in zones])
 
 
+def gen_meta():
+    """SfMeta / SfContours per-zone statistics, from the UNMODIFIED reference:
+      * SfContours.find_stones (sf_contours.py:48-111) on a synthetic board + foreground blob: the `zones` table it builds
+        (visible flag + int16 mean B, G, R per zone, _norm_channels :113-126) and the `mask` of filled convex hulls it was
+        computed from. The reference targets OpenCV 3 (`_, contours, hierarchy = cv2.findContours(..)`): under cv2 4.x
+        the call is wrapped to return three values; `zones` / `mask` are locals, captured through wrappers around
+        SfContours.find_color and cv2.drawContours. Nothing in the reference is edited.
+      * Region.commit (sf_meta.py:305-340) on random detection histories: the moves it submits.
+      * Region.check_foreground (sf_meta.py:342-381) for the 3 x 3 regions on random foreground masks."""
+    import cv2
+    from oracle import refimport
+    from camkifu_b200 import synth
+    refimport.load()
+    from camkifu.core import imgutil
+    from camkifu.stone.sf_contours import SfContours
+    from camkifu.stone.sf_meta import Region, SfMeta
+    out = {}
+    # ---- zone means
+    _fc, _dc = cv2.findContours, cv2.drawContours
+
+    def fc3(*a, **k):
+        r = _fc(*a, **k)
+        return (None,) + tuple(r) if len(r) == 2 else r
+
+    cap = {}
+
+    def dc(img, conts, idx, color=None, **kw):
+        if isinstance(color, tuple) and tuple(color) == (1, 1, 1) and kw.get("thickness") == -1:
+            cap["mask"] = img
+        return _dc(img, conts, idx, color, **kw) if color is not None else _dc(img, conts, idx, **kw)
+
+    orig_find_color = SfContours.find_color
+
+    def rec(r, c, zones, stones):
+        cap["zones"] = zones.copy()
+        return orig_find_color(r, c, zones, stones)
+
+    cv2.findContours, cv2.drawContours = fc3, dc
+    SfContours.find_color = staticmethod(rec)
+    try:
+        frames, mtx, truth, _ = synth.make_clip(31, 2, 360, 480)
+        for k, (rs, re, cs, ce) in enumerate(((0, 19, 0, 19), (6, 13, 0, 7))):
+            g = cv2.warpPerspective(frames[k], mtx, (380, 380))
+            sf = SfContours(refimport.FakeVManager(mtx))
+            sf.total_f_processed = 100
+            fg = np.zeros((380, 380), np.uint8)
+            cv2.circle(fg, (150, 90), 9, 255, -1)
+            sf._fg = fg
+            cap.clear()
+            stones = sf.find_stones(g, rs=rs, re=re, cs=cs, ce=ce)
+            x0, y0 = sf.getrect(rs, cs)[:2]
+            x1, y1 = sf.getrect(re - 1, ce - 1)[2:]
+            full = np.zeros((380, 380), np.uint8)
+            full[x0:x1, y0:y1] = cap["mask"][:, :, 0]
+            out["zm_img_%d" % k], out["zm_mask_%d" % k] = g, full
+            out["zm_region_%d" % k] = np.array([rs, re, cs, ce])
+            out["zm_zones_%d" % k] = cap["zones"]
+            out["zm_stones_%d" % k] = codes(stones)
+    finally:
+        cv2.findContours, cv2.drawContours = _fc, _dc
+        SfContours.find_color = staticmethod(orig_find_color)
+
+    # ---- Region.commit / check_foreground with a scripted finder
+    class FakeSf:
+        contour, cluster = "contour", "cluster"
+
+        def __init__(self, base):
+            self.base, self.empty, self.fg, self.sent = base, None, None, []
+
+        def is_empty(self, r, c):
+            return bool(self.empty[r, c])
+
+        def bulk_update(self, moves):
+            self.sent.extend(moves)
+
+        def suggest(self, color, r, c, doprint=True):
+            self.sent.append((color, r, c))
+
+        def get_foreground(self):
+            return self.fg
+
+        def getrect(self, r, c, cursor=1.0):
+            return self.base.getrect(r, c, cursor)
+
+        def stone_radius(self):
+            return self.base.stone_radius()
+
+    base = SfContours(refimport.FakeVManager(None))
+    fake = FakeSf(base)
+    bounds = [SfMeta.subregion(type("S", (), {"split": 3})(), r, c) for r in range(3) for c in range(3)]
+    out["regions"] = np.array(bounds)
+    rng = np.random.default_rng(7)
+    hist_all, empty_all, moves_all = [], [], []
+    colors = np.array(['E', 'B', 'W'], dtype=object)
+    for trial in range(6):
+        histo = 3 if trial < 4 else 5
+        hist = np.zeros((19, 19, histo), np.uint8)
+        moves = np.zeros((19, 19), np.uint8)
+        fake.empty = rng.random((19, 19)) < 0.8
+        for (rs, re, cs, ce) in bounds:
+            reg = Region(fake, (rs, re, cs, ce), histo, finder=None, state="search")
+            cb = imgutil.CyclicBuffer((re - rs, ce - cs), histo, dtype=object, init='E')
+            h = rng.choice(3, size=(re - rs, ce - cs, histo), p=(0.5, 0.3, 0.2)).astype(np.uint8)
+            stable = rng.random((re - rs, ce - cs)) < 0.4           # many intersections agree across the history
+            h[stable] = h[stable][:, :1]
+            from golib.config.golib_conf import E, B, W
+            lut = np.array([E, B, W], dtype=object)
+            cb.buffer[:] = lut[h]
+            fake.sent = []
+            reg.commit(cb)
+            for col, r, c in fake.sent:
+                moves[r, c] = CODE[col]
+            hist[rs:re, cs:ce] = h
+        hist_all.append(hist if histo == 3 else hist)
+        empty_all.append(fake.empty.astype(np.uint8))
+        moves_all.append(moves)
+    for i in range(6):
+        out["vote_hist_%d" % i], out["vote_empty_%d" % i], out["vote_moves_%d" % i] = hist_all[i], empty_all[i], moves_all[i]
+    calm = []
+    fgs = []
+    for trial in range(12):
+        fg = np.zeros((380, 380), np.uint8)
+        for _ in range(int(rng.integers(0, 5))):
+            ctr = (int(rng.integers(0, 380)), int(rng.integers(0, 380)))
+            cv2.circle(fg, ctr, int(rng.integers(4, 40)), 255, -1)
+        if trial % 4 == 3:
+            cv2.rectangle(fg, (0, 0), (25, 25), 255, -1)              # a corner zone
+        fake.fg = fg
+        row = []
+        for (rs, re, cs, ce) in bounds:
+            reg = Region(fake, (rs, re, cs, ce), 3, finder=None, state="search")
+            row.append(bool(reg.check_foreground()))
+        calm.append(row)
+        fgs.append(np.packbits(fg > 0))
+    out["fg_masks"], out["fg_calm"] = np.array(fgs), np.array(calm)
+    np.savez_compressed(os.path.join(GOLD, "meta.npz"), **out)
+    print("meta: zones visible", int(out["zm_zones_0"][:, :, 0].sum()), "votes", [int((m > 0).sum()) for m in moves_all],
+          "calm", np.array(calm).mean())
+
+
 def gen_neural_stream():
     import cv2
     from oracle import refimport
@@ -278,6 +421,8 @@ if __name__ == "__main__":
         gen_background()
     elif what == "neural_stream":
         gen_neural_stream()
+    elif what == "meta":
+        gen_meta()
     elif what == "all":
         for g in (9, 13, 19):
             subprocess.run([sys.executable, "-m", "oracle.gen_golden", "geometry"], check=True, cwd=ROOT,
@@ -286,3 +431,4 @@ if __name__ == "__main__":
         gen_neural()
         gen_background()
         gen_neural_stream()
+        gen_meta()

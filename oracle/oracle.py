@@ -277,3 +277,99 @@ def torch_cnn(params):
             z = h @ w6 + b6
             return torch.softmax(z, dim=1).numpy()
     return predict
+
+
+# --------------------------------------------------------------------------- SfMeta / SfContours zone statistics (f4)
+def meta_subregions(gsize=19, split=3):
+    """SfMeta.subregion for every (row, col) (sf_meta.py:101-125): [(rs, re, cs, ce)] row-major."""
+    step = int(gsize / split)
+    out = []
+    for row in range(split):
+        for col in range(split):
+            re, ce = (row + 1) * step, (col + 1) * step
+            if gsize - re < step:
+                re = gsize
+            if gsize - ce < step:
+                ce = gsize
+            out.append((row * step, re, col * step, ce))
+    return out
+
+
+def meta_zone_means(img, mask, gsize=19, rs=0, re=None, cs=0, ce=None):
+    """The zone table of SfContours.find_stones (sf_contours.py:87-102) with _norm_channels (:113-126).
+    img (S, S, 3) uint8; mask (S, S) 0/1 in canonical coordinates. Returns int16 (re-rs, ce-cs, 4)."""
+    re = gsize if re is None else re
+    ce = gsize if ce is None else ce
+    rects = c_zone_rects(gsize)
+    m3 = (mask != 0).astype(np.uint8)[:, :, None]
+    visible_sub, masked_sub = img * m3, img * (1 - m3)
+    zones = np.zeros((re - rs, ce - cs, 4), dtype=np.int16)
+    for r in range(re - rs):
+        for c in range(ce - cs):
+            a0, b0, a1, b1 = (int(v) for v in rects[r + rs, c + cs])
+            area = (a1 - a0) * (b1 - b0)
+            visible_area = int(np.sum(m3[a0:a1, b0:b1, 0]))
+            if 0.4 * area < visible_area:
+                zones[r, c, 0] = 1
+                src, norm = visible_sub[a0:a1, b0:b1], visible_area
+            else:
+                src, norm = masked_sub[a0:a1, b0:b1], area - visible_area
+            for k in range(3):
+                zones[r, c, k + 1] = int(int(np.sum(src[:, :, k])) / norm)
+    return zones
+
+
+def meta_vote(hist, empty):
+    """Region.commit's per-intersection rule (sf_meta.py:318-331). hist (..., histo) uint8 codes, empty (...) bool.
+    Returns uint8 move codes (0 = none, 1 = B, 2 = W)."""
+    hist = np.asarray(hist)
+    out = np.zeros(hist.shape[:-1], np.uint8)
+    size = hist.shape[-1]
+    for idx in np.ndindex(*hist.shape[:-1]):
+        if not empty[idx]:
+            continue
+        vals, counts = np.unique(hist[idx], return_counts=True)
+        if len(vals) == 2 and 0 in vals:
+            k = 0 if vals[0] == 0 else 1
+            if counts[k] / size < 0.4:
+                out[idx] = vals[1 - k]
+        elif len(vals) == 1 and 0 not in vals:
+            out[idx] = vals[0]
+    return out
+
+
+def meta_outer_border(rs, re, cs, ce, gsize=19):
+    """Region.outer_border (sf_meta.py:444-463): the (row, col) of the zones around the region, in the reference's order."""
+    out = []
+    x = max(0, cs - 1)
+    for y in range(max(0, rs - 1), min(gsize, re + 1)):
+        out.append((y, x))
+    y = min(gsize - 1, re)
+    for x in range(max(1, cs), min(gsize, ce + 1)):
+        out.append((y, x))
+    x = min(gsize - 1, ce)
+    for y in range(min(gsize - 2, re - 1), max(-1, rs - 2), -1):
+        out.append((y, x))
+    y = max(0, rs - 1)
+    for x in range(min(gsize - 2, ce - 1), max(0, cs - 1), -1):
+        out.append((y, x))
+    return out
+
+
+def meta_check_foreground(fg, rs, re, cs, ce, gsize=19):
+    """Region.check_foreground (sf_meta.py:342-381) on a foreground mask (0 / 255): True = calm."""
+    import math
+    rects = c_zone_rects(gsize)
+    moving, border_threshold = 0, 2
+    for (r, c) in meta_outer_border(rs, re, cs, ce, gsize):
+        a0, b0, a1, b1 = (int(v) for v in rects[r, c])
+        if (a1 - a0) * (b1 - b0) * 0.7 < np.sum(fg[a0:a1, b0:b1]) / 255:
+            if (a0 == 0 or a1 == fg.shape[0] - 1) and (b0 == 0 or b1 == fg.shape[1] - 1):
+                moving = border_threshold
+            moving += 1
+            if border_threshold <= moving:
+                return False
+    x0, y0 = rects[rs, cs, 0], rects[rs, cs, 1]
+    x1, y1 = rects[re - 1, ce - 1, 2], rects[re - 1, ce - 1, 3]
+    threshold = 3 * ((fg.shape[0] / gsize / 2) ** 2) * math.pi
+    return not (threshold < np.sum(fg[x0:x1, y0:y1]) / 255)
