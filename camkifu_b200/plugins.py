@@ -168,6 +168,21 @@ class _DeviceFrames:
         eng.upload_frames(torch.from_numpy(frame)[None], self._d_frame, eng.frame_roi(mtx, frame.shape[0], frame.shape[1]))
         return self._d_frame
 
+    def _fetch(self, **tensors):
+        """Device tensors -> numpy arrays with ONE synchronisation: every copy goes into a pinned staging buffer of its
+        own on the current stream, then the stream is waited for once (a `.cpu()` per tensor would block per tensor).
+        The arrays are copies: they stay valid after the next frame."""
+        torch = self._torch
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        for k, t in tensors.items():
+            buf = self._pinned.get(k)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = self._pinned[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self._engine_obj.device).synchronize()
+        return {k: self._pinned[k].numpy().copy() for k in tensors}
+
     def _device_image(self, img: np.ndarray):
         """The device copy of a canonical image: the one just warped when `img` is that very array, else an upload."""
         if img is self.goban_img and getattr(self, "_goban_on_device", False):
@@ -191,9 +206,12 @@ class _DeviceFrames:
             still = isinstance(video, str) and video.lower().endswith((".png", ".jpg", ".jpeg"))
             self.bg_init_frames = 0 if still else 50          # stonesfinder.py:115
 
-    def _learn_bg(self):
+    def _learn_bg(self, fetch: bool = True):
+        """Enqueue the background-model update of the frame just warped; returns the device tensor of per-zone foreground
+        counts (None when the model is off). fetch=False leaves the read-back to the caller (_doframe reads it together
+        with the canonical image: one synchronisation per frame)."""
         if not self._bg_on:
-            return
+            return None
         if not getattr(self, "_goban_on_device", False):
             raise RuntimeError("the background model runs on the device image produced by _doframe")
         eng = self._engine()
@@ -203,8 +221,11 @@ class _DeviceFrames:
         learning = 0.01 if self.total_f_processed < self.bg_init_frames else 0.005      # stonesfinder.py:174
         eng.mog2_apply(self._d_goban, self._bg_state, self._bg_frames, [learning], out=self._d_fg)
         self._bg_frames += 1
-        self._zone_fg = eng.zone_fg_counts(self._d_fg)[0].cpu().numpy()
+        d_counts = eng.zone_fg_counts(self._d_fg)
         self._fg_host = None
+        if fetch:
+            self._zone_fg = self._fetch(zone_fg=d_counts)["zone_fg"][0]
+        return d_counts
 
     def get_foreground(self):
         """The foreground mask of the last frame, (S, S) uint8 0 / 255 (stonesfinder.py:502-515)."""
@@ -232,9 +253,14 @@ class _DeviceFrames:
             return
         eng = self._engine()
         eng.warp(self._upload_frame(frame, transform), transform, out=self._d_goban)
-        self.goban_img = self._d_goban[0].cpu().numpy()
         self._goban_on_device = True
-        self._learn_bg()
+        d_counts = self._learn_bg(fetch=False)       # background model enqueued behind the warp
+        if d_counts is not None:
+            got = self._fetch(goban=self._d_goban, zone_fg=d_counts)
+            self._zone_fg = got["zone_fg"][0]
+        else:
+            got = self._fetch(goban=self._d_goban)
+        self.goban_img = got["goban"][0]
         self._learn()
         self._find(self.goban_img)
 
@@ -286,9 +312,28 @@ def build_classes(Base):
                 self.rng_state = rng_seed(0)
             res = eng.find_stones(d_img, [self.rng_state], rs, re, cs, ce)
             self.rng_state = rng_advance(self.rng_state, 1)
-            if not bool(res["trusted"][0].item()):
+            got = self._fetch(km_stones=res["stones"], km_trusted=res["trusted"])
+            if not bool(got["km_trusted"][0]):
                 return None
-            return stones_from_codes(res["stones"][0].cpu().numpy())
+            return stones_from_codes(got["km_stones"][0])
+
+        def find_stones_regions(self, img, regions):
+            """find_stones(img, rs, re, cs, ce) for every (rs, re, cs, ce) of `regions` (at most 16) in one set of
+            launches: what SfMeta's 3 x 3 Regions ask of their `cluster` delegate on one frame (sf_meta.py:245-262),
+            without nine serial calls. The RNG stream advances region after region, as the serial calls would. Returns
+            a list with, per region, the (19, 19) object array of 'E' / 'B' / 'W' or None (density check failed)."""
+            from .engine import rng_seed, rng_advance, rng_states
+            eng = self._engine()
+            if img.dtype != np.uint8:
+                return [self.find_stones(img, *r) for r in regions]      # float32 images: one region per call
+            if self.rng_state is None:
+                self.rng_state = rng_seed(0)
+            states = rng_states(self.rng_state, 0, len(regions))
+            res = eng.find_stones_regions(self._device_image(img), regions, [states])
+            self.rng_state = rng_advance(self.rng_state, len(regions))
+            got = self._fetch(kmr_stones=res["stones"], kmr_trusted=res["trusted"])
+            return [stones_from_codes(got["kmr_stones"][0, k]) if got["kmr_trusted"][0, k] else None
+                    for k in range(len(regions))]
 
         def find_stones(self, img, rs=0, re=gsize, cs=0, ce=gsize, **kwargs):
             """SfClustering.find_stones (sf_clustering.py:48-75). img: (S, S, 3) uint8 or float32 canonical image."""
@@ -333,8 +378,9 @@ def build_classes(Base):
             if not self._weights_loaded:
                 self._load_net()
             out = self._engine().cnn_forward(self._device_image(goban_img))
-            self.cache = NNCacheB200(out["softmax"][0].cpu().numpy())
-            self._last = {k: out[k][0].cpu().numpy() for k in ("stones", "conf", "keep")}
+            got = self._fetch(softmax=out["softmax"], nn_stones=out["stones"], nn_conf=out["conf"], nn_keep=out["keep"])
+            self.cache = NNCacheB200(got["softmax"][0])
+            self._last = {"stones": got["nn_stones"][0], "conf": got["nn_conf"][0], "keep": got["nn_keep"][0]}
             return self.cache
 
         def _find(self, goban_img):

@@ -231,3 +231,22 @@ def test_sfclustering_keeps_a_background_model(golden):
         fg = sf.get_foreground()
         assert fg.shape == (380, 380) and np.array_equal(np.packbits(fg > 0), g["masks"][i]), "frame %d" % i
     assert sf.is_agitated(*np.unravel_index(int(g["zone_fg"][11].argmax()), (19, 19)))
+
+
+def test_sfclustering_regions_delegate_equals_serial_calls(golden):
+    """SfMeta's nine regions on one frame: the batched delegate call returns what nine find_stones calls return, in the
+    same RNG order, and leaves the finder's RNG state where the serial calls leave it."""
+    from camkifu_b200 import meta
+    g = golden("clustering_full.npz")
+    regions = meta.subregions()
+    a, b = plugins.SfClusteringB200(None), plugins.SfClusteringB200(None)
+    a.set_rng_seed(77)
+    b.set_rng_seed(77)
+    serial = [a.find_stones(g["goban_0"], *r) for r in regions]
+    batched = b.find_stones_regions(g["goban_0"], regions)
+    assert a.rng_state == b.rng_state
+    for s, t in zip(serial, batched):
+        assert (s is None) == (t is None)
+        if s is not None:
+            assert np.array_equal(codes(s), codes(t))
+    assert any(s is not None for s in serial)
