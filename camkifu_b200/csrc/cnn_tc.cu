@@ -39,10 +39,10 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
                           float *d_conf, uint8_t *d_keep, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------ layer configs
-struct Conv1Cfg {   // input: 16-channel "row window" expansion of the patch (k = dx*3 + c), taps = dy
+struct Conv1Cfg {   // geometry only (weights size), as Conv2Cfg: input = 16-channel "row window" expansion (k = dx*3 + c), taps = dy
     static constexpr int NTAPS = 5, GW = 40, HW_IN = 1600, OH = 36, OW = 36, KC = 2, N = 32, A_PLANES = 1;
     static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
-    static constexpr int KCS = 2, NSTAGE = 1, NABUF = 6, NACC = 4;   // tiny tiles: latency bound without depth
+    static constexpr int KCS = 2, NSTAGE = 1, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
 };
 struct Conv2Cfg {   // geometry only (weights size): conv1 and conv2 run in cnn_tc_front.cu, not through cnn_tc_layer

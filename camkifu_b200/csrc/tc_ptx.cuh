@@ -101,14 +101,6 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 __device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
-// 4-D tiled tensor-map load (TMA): box -> shared memory, completion on an mbarrier
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c0, int c1, int c2, int c3, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
 // instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc(int n)
 {

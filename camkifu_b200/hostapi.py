@@ -9,7 +9,6 @@ conventions and error behaviour, written from the interface description — only
 
 Coordinates: (r, c) numpy row / column in finders; controller calls take (x = c, y = r) (stonesfinder.py:305,349).
 """
-import queue
 
 import numpy as np
 
@@ -47,16 +46,6 @@ class DeletedError(ValueError):
         self.message = message
 
 
-class CorrectionWarning(Warning):
-    """camkifu.core.exceptions.CorrectionWarning (exceptions.py:22-43): user corrections the finder did not learn from."""
-
-    def __init__(self, corrections, message=None):
-        text = "{}" if message is None else str(message)
-        text += " [" + ", ".join("(err:{}, exp:{})".format(e, x) for e, x in corrections) + "]"
-        super().__init__(text)
-        self.corrections = corrections
-
-
 def zone_rect(r: int, c: int, g: int = gsize):
     """StonesFinder.getrect(r, c, cursor=1.0) (stonesfinder.py:412-450): intersections sit at 10 + 20 k, a zone spans
     the 20 pixels around one, the last row / column stop one pixel short of the image edge."""
@@ -80,12 +69,6 @@ class PosGridMirror:
                 self.mtx[i, j, 0] = (first * (g - 1 - i) + last * i) / (g - 1)
                 self.mtx[i, j, 1] = (first * (g - 1 - j) + last * j) / (g - 1)
 
-    def closest_intersection(self, point):
-        """Row and column of the intersection nearest to the (x, y) point of the canonical image."""
-        d = (self.mtx[:, :, 0].astype(np.int64) - point[0]) ** 2 + (self.mtx[:, :, 1].astype(np.int64) - point[1]) ** 2
-        i, j = np.unravel_index(int(np.argmin(d)), d.shape)
-        return int(i), int(j)
-
 
 class StonesFinderBase:
     """Mirror of camkifu.stone.StonesFinder + the bits of camkifu.core.video.VidProcessor finders rely on."""
@@ -104,10 +87,6 @@ class StonesFinderBase:
             video = getattr(vmanager, "current_video", None)
             is_img = isinstance(video, str) and video.lower().endswith((".png", ".jpg", ".jpeg"))
             self.bg_init_frames = 0 if is_img else 50
-        self.corrections = queue.Queue(10)          # user corrections, filled from the GUI thread (see corrected())
-        self.saved_bg = np.zeros(self.canonical_shape + (3,), dtype=np.float32)
-        self.deleted = {}
-        self.nb_del_samples = 50
 
     # ---- frame loop hooks
     def ready_to_read(self):
@@ -123,43 +102,10 @@ class StonesFinderBase:
     def _learn_bg(self):
         pass   # the B200 plugins keep the MOG2 background model on the device (plugins._DeviceFrames._learn_bg)
 
-    def corrected(self, err_move, exp_move):
-        """StonesFinder.corrected (stonesfinder.py:323-339): the user removed `err_move` and / or added `exp_move`; the
-        finder's own thread digests it in _learn()."""
-        try:
-            self.corrections.put_nowait((err_move, exp_move))
-        except queue.Full:
-            print("Corrections queue full (%s), ignoring %s -> %s" % (self.corrections.maxsize, err_move, exp_move))
-
     def _learn(self):
-        """StonesFinder._learn (stonesfinder.py:178-221). A location the user emptied (a deletion, or the source of a
-        relocation) is put under watch: its appearance is averaged over the next `nb_del_samples` calm frames into
-        `saved_bg`, and until the zone looks different again suggestions there are refused (_check_dels). Corrections of
-        another kind (a stone the detection missed) are reported with a CorrectionWarning, as in the reference."""
-        unhandled = []
-        while True:
-            try:
-                err, exp = self.corrections.get_nowait()
-            except queue.Empty:
-                break
-            if exp is None or (err is not None and (err.x, err.y) != (exp.x, exp.y)):
-                self.deleted[(err.y, err.x)] = self.nb_del_samples
-            else:
-                unhandled.append((err, exp))
-        for (r, c), left in self.deleted.items():
-            if not left:
-                continue
-            try:
-                fg = self.get_foreground()
-            except ValueError:
-                fg = None
-            x0, y0, x1, y1 = self.getrect(r, c)
-            # the reference's test reads np.sum(fg[zone] < 0.1 * area): the number of mask values below that threshold
-            if fg is None or np.sum(fg[x0:x1, y0:y1] < 0.1 * (x1 - x0) * (y1 - y0)):
-                self.saved_bg[x0:x1, y0:y1] += self.goban_img[x0:x1, y0:y1] / self.nb_del_samples
-                self.deleted[(r, c)] = left - 1
-        if unhandled:
-            raise CorrectionWarning(unhandled, message="Unhandled corrections")
+        """Hook of the frame loop (stonesfinder.py:178). The reference's base class digests user corrections here
+        (deletion watch, CorrectionWarning): GUI-driven, out of scope for the detection path; both
+        B200 finders override it with a no-op exactly as SfClustering does (sf_clustering.py:180-181)."""
 
     def get_foreground(self):
         raise ValueError("This StonesFinder doesn't seem to be segmenting background. See self.__init__()")
@@ -202,22 +148,7 @@ class StonesFinderBase:
     def get_stones(self):
         return self.vmanager.controller.get_stones()
 
-    def _check_dels(self, r, c):
-        """StonesFinder._check_dels (stonesfinder.py:223-245): refuse a location under deletion watch until its zone
-        differs from what was sampled after the deletion by 40 grey levels per pixel on average."""
-        if (r, c) not in self.deleted:
-            return
-        if self.deleted[(r, c)] != 0:
-            raise DeletedError(((r, c),), "The zone has been marked as deleted too recently.")
-        x0, y0, x1, y1 = self.getrect(r, c)
-        diff = self.saved_bg[x0:x1, y0:y1] - self.goban_img[x0:x1, y0:y1]
-        if np.sum(np.absolute(diff)) / (diff.shape[0] * diff.shape[1]) < 40:
-            raise DeletedError(((r, c),), "The zone has not changed enough since last deletion.")
-        print("previously user-deleted location: {} now unlocked".format((r, c)))
-        del self.deleted[(r, c)]
-
     def suggest(self, color, r, c, doprint=True):
-        self._check_dels(r, c)
         move = Move('np', ctuple=(color, r, c))
         if doprint:
             print(move)
@@ -231,8 +162,10 @@ class StonesFinderBase:
 
     def bulk_update(self, tuples):
         """E on an occupied point removes the stone; B / W on an empty point adds one; on a point of the other colour
-        the old stone is removed first; unchanged points are skipped. One "bulk" + "auto_save" for the lot."""
-        moves, del_errors = [], []
+        the old stone is removed first; unchanged points are skipped. One "bulk" + "auto_save" for the lot. (The
+        reference's base class also refuses locations the user has just deleted in the GUI — DeletedError, raised by the
+        reference's own StonesFinder when the plugins inherit from it; this stand-alone mirror has no GUI to learn from.)"""
+        moves = []
         for color, r, c in tuples:
             occupied = not self.is_empty(r, c)
             if color is E or color == E:
@@ -245,13 +178,7 @@ class StonesFinderBase:
                 if self.vmanager.controller.locate(c, r).color == color:
                     continue
                 moves.append(Move('np', (E, r, c)))
-            try:
-                self._check_dels(r, c)
-                moves.append(Move('np', (color, r, c)))
-            except DeletedError as de:
-                del_errors.append(de)
+            moves.append(Move('np', (color, r, c)))
         if moves:
             self.vmanager.controller.pipe("bulk", moves)
             self.vmanager.controller.pipe("auto_save")
-        if del_errors:
-            raise DeletedError(del_errors, message="Bulk_update:warning: All non-conflicting locations have been sent.")

@@ -62,10 +62,6 @@ def test_mirror_geometry_and_bulk_update(golden, base):
     assert last == [('E', 3, 4), ('W', 3, 4), ('E', 5, 6)]
     assert ctl.stones[3, 4] == 'W' and ctl.stones[5, 6] == 'E'
     assert ctl.piped[-1][0] == "auto_save"
-    sf.deleted[(9, 9)] = True
-    with pytest.raises(hostapi.DeletedError):
-        sf.bulk_update([('B', 9, 9), ('B', 10, 10)])
-    assert ctl.stones[10, 10] == 'B' and ctl.stones[9, 9] == 'E'   # non-conflicting locations were sent
 
 
 def test_plugins_construct_without_gpu_and_tolerate_no_vmanager():
@@ -126,74 +122,9 @@ def test_heat_point_mirrors_reference():
             assert (a == sfn.HeatPoint) == b.live and (a == sfn.COLD) == b.is_cold()
 
 
-def test_user_correction_learning_mirrors_reference():
-    """hostapi.StonesFinderBase.corrected / _learn / _check_dels against the reference's StonesFinder
-    (stonesfinder.py:178-245,323-339): same deletion watch, same sampled background, same refusals."""
-    from oracle import refimport
-    if not refimport.available():
-        pytest.skip("reference tree not present")
-    refimport.load()
-    from camkifu.stone.stonesfinder import StonesFinder
-    import camkifu.core
-    from camkifu_b200 import hostapi
-
-    class Ref(StonesFinder):
-        def _find(self, img):
-            pass
-
-    class Mir(hostapi.StonesFinderBase):
-        def _find(self, img):
-            pass
-
-    ref = Ref(refimport.FakeVManager(None), learn_bg=False)
-    mir = Mir(refimport.FakeVManager(None), learn_bg=False)
-    mir.nb_del_samples = ref.nb_del_samples = 4
-    rng = np.random.default_rng(3)
-    base = rng.integers(0, 256, (380, 380, 3), dtype=np.uint8)
-    err = hostapi.Move('np', ('B', 4, 7))
-    added = hostapi.Move('np', ('W', 9, 9))
-    for f in (ref, mir):
-        f.goban_img = base.copy()
-        f.corrected(err, None)                                  # the user deleted a stone at row 4, column 7
-    for step in range(6):
-        img = np.clip(base.astype(np.int16) + rng.integers(-3, 4, base.shape), 0, 255).astype(np.uint8)
-        for f in (ref, mir):
-            f.goban_img = img
-            f._learn()
-        assert ref.deleted == mir.deleted == {(4, 7): max(0, 4 - step - 1)}
-        assert np.array_equal(ref.saved_bg, mir.saved_bg)
-        for f, exc in ((ref, camkifu.core.DeletedError), (mir, hostapi.DeletedError)):
-            with pytest.raises(exc):
-                f._check_dels(4, 7)                             # too recent, then "has not changed enough"
-            f._check_dels(5, 7)                                 # other locations are free
-    changed = base.copy()
-    changed[80:100, 140:160] = 255 - changed[80:100, 140:160]   # a real stone appears in the zone: the watch is lifted
-    for f in (ref, mir):
-        f.goban_img = changed
-        f._check_dels(4, 7)
-        assert f.deleted == {}
-    for f, warn in ((ref, camkifu.core.CorrectionWarning), (mir, hostapi.CorrectionWarning)):
-        f.corrected(None, added)                                # a missed stone: reported, not learnt from
-        with pytest.raises(warn):
-            f._learn()
-
-
 def test_posgrid_mirror_matches_reference(golden):
-    """hostapi.PosGridMirror against PosGrid.mtx recorded from the reference (geometry_g19.npz) and, when the reference is
-    importable, against PosGrid.closest_intersection on random points."""
+    """hostapi.PosGridMirror against PosGrid.mtx recorded from the reference (geometry_g19.npz)."""
     from camkifu_b200 import hostapi
     g = golden("geometry_g19.npz")
     pg = hostapi.PosGridMirror(380)
     assert pg.mtx.dtype == np.int16 and np.array_equal(pg.mtx, g["posgrid"])
-    from oracle import refimport
-    if refimport.available():
-        refimport.load()
-        from camkifu.stone.stonesfinder import PosGrid
-        ref = PosGrid(380)
-        rng = np.random.default_rng(0)
-        for _ in range(200):
-            pt = (int(rng.integers(0, 380)), int(rng.integers(0, 380)))
-            a, b = ref.closest_intersection(pt), pg.closest_intersection(pt)
-            da = (int(ref.mtx[a[0], a[1], 0]) - pt[0]) ** 2 + (int(ref.mtx[a[0], a[1], 1]) - pt[1]) ** 2
-            db = (int(pg.mtx[b[0], b[1], 0]) - pt[0]) ** 2 + (int(pg.mtx[b[0], b[1], 1]) - pt[1]) ** 2
-            assert da == db          # the same distance (ties between equidistant intersections may resolve differently)
