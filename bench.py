@@ -497,7 +497,10 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     vpipe = DetectPipeline(H, W, GSIZE, mode="neural", sub_batch=16, engine=eng)
     vmem_frames = args.video_frames * world
     cores = os.cpu_count() or 1
-    decoders = max(1, min(8, cores // world - 1))
+    # decoder threads per rank: each owns a capture and seeks once; OpenCV's FFmpeg seek decodes ~16 frames at best and
+    # for some frame numbers falls back to decoding from the start of the file (measured: 0.15 s .. 2 s per seek on this
+    # 512-frame file, tools/_probe notes in DESIGN.md), so more than a few captures per rank cost more than they give
+    decoders = max(1, min(4, cores // world - 1))
     vfile = os.path.join("/tmp", "ckb_bench_%s.avi" % os.environ.get("MASTER_PORT", "single"))
     vfile_frames = 512
     if rank == 0:
@@ -610,7 +613,8 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
                        "weights": "glorot_uniform seed 0 (reference architecture, nn_manager.py:277-298)",
                        "l2": "inputs larger than L2: two resident 398 MB batches used alternately",
                        "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world,
-                       "gpu_map": gpu_map, "numa_bound": numa_bound, "tolerance": SOFTMAX_TOLERANCE},
+                       "gpu_map": gpu_map, "numa_bound": numa_bound, "cpus_available_to_rank0": len(os.sched_getaffinity(0)),
+                       "tolerance": SOFTMAX_TOLERANCE},
             "value_sustained": {"value": fps(sus_n, sus_ms), "unit": UNIT, "steps": sus_n, "seconds": sus_ms / 1e3,
                                 "clocks": sus_clocks},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -670,8 +674,10 @@ def main():
         run_reference(args, rank, world)
         return
     # LOCAL_RANK -> physical GPU by PCIe topology: with fewer ranks than GPUs, spread them over distinct host uplinks
-    from camkifu_b200.affinity import pick_gpus
-    gpu_map = pick_gpus(world) if world > 1 else [local_rank]
+    # (measured: NVML's topology levels do not tell the switches of these boxes apart — camkifu_b200.affinity)
+    from camkifu_b200.affinity import gpu_map_for_run
+    token = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+    gpu_map, map_info = gpu_map_for_run(world, local_rank, token) if world > 1 else ([local_rank], None)
     gpu_index = gpu_map[local_rank] if local_rank < len(gpu_map) else local_rank
     if world > 1:
         import torch
@@ -680,7 +686,7 @@ def main():
         torch.cuda.set_device(gpu_index)
         dist.init_process_group("nccl", device_id=torch.device("cuda", gpu_index))
     try:
-        run_b200(args, rank, world, local_rank, gpu_index, gpu_map)
+        run_b200(args, rank, world, local_rank, gpu_index, {"map": gpu_map, "probe": map_info})
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -4,19 +4,23 @@ memory that sits on the other socket costs a large part of the aggregate host-to
 import os
 
 
-def bind_to_gpu(index: int) -> bool:
-    """Pin the calling process to the CPU set NVML reports as local to GPU `index` (nvmlDeviceSetCpuAffinity).
-    Returns False (and changes nothing) when NVML or the affinity call is unavailable, e.g. inside a restricted cgroup."""
+def bind_to_gpu(index: int, min_cpus: int = 4) -> bool:
+    """Pin the calling process to the CPU set NVML reports as local to GPU `index` (nvmlDeviceSetCpuAffinity), when that
+    helps: only if the set NVML would install is a proper subset of the CPUs the process may use now (i.e. the box really
+    has several NUMA nodes) and still holds at least `min_cpus` CPUs — the decoder threads of the offline-video path
+    live in this process. Returns False (and changes nothing) otherwise, or when NVML / the affinity call is
+    unavailable, e.g. inside a restricted cgroup."""
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         before = os.sched_getaffinity(0)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        after = os.sched_getaffinity(0)
-        if not after:                      # never leave the process without CPUs
-            os.sched_setaffinity(0, before)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(before) // 64) + 1)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        target = ideal & before
+        if len(target) < min_cpus or target == before:
             return False
+        os.sched_setaffinity(0, target)
         return True
     except Exception:
         return False
@@ -57,3 +61,94 @@ def pick_gpus(world: int, levels=None):
                 best, best_key = g, key
         chosen.append(best)
     return chosen
+
+
+def measure_uplink_groups(n_gpus: int = None, mbytes: int = 64, reps: int = 4):
+    """Which GPUs share a host uplink, MEASURED: NVML reports every GPU pair of these boxes at the same PCIe level, yet
+    four ranks on GPUs 0-3 get the host -> device bandwidth of two links. For a reference GPU and each other GPU, copy
+    pinned host buffers to both at once: two GPUs behind one switch split one link's bandwidth (aggregate ~ 1 x a single
+    copy), two on separate links add up (~ 2 x). Returns (groups, table): groups = lists of GPU indices per uplink,
+    table = {(i, j): GB/s} of what was measured. Creates a CUDA context on every GPU: call from ONE process."""
+    import time
+    import torch
+    n = torch.cuda.device_count() if n_gpus is None else n_gpus
+    nbytes = mbytes << 20
+    host = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    dev = [torch.empty(nbytes, dtype=torch.uint8, device="cuda:%d" % g) for g in range(n)]
+    streams = [torch.cuda.Stream(device="cuda:%d" % g) for g in range(n)]
+
+    def run(gpus):
+        for _ in range(2):                                   # warm-up, then timed
+            for g in gpus:
+                torch.cuda.synchronize(g)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for k, g in enumerate(gpus):
+                    with torch.cuda.stream(streams[g]):
+                        dev[g].copy_(host[k], non_blocking=True)
+            for g in gpus:
+                streams[g].synchronize()
+            dt = time.perf_counter() - t0
+        return len(gpus) * reps * nbytes / dt / 1e9
+
+    table, groups, left = {}, [], list(range(n))
+    while left:
+        ref = left.pop(0)
+        single = table[(ref, ref)] = run([ref])
+        grp = [ref]
+        for g in list(left):
+            both = table[(ref, g)] = run([ref, g])
+            if both < 1.5 * single:
+                grp.append(g)
+                left.remove(g)
+        groups.append(grp)
+    return groups, table
+
+
+def spread_over_groups(world: int, groups):
+    """`world` GPUs, taken round-robin from the uplink groups (one from each before a second from any)."""
+    order, depth = [], 0
+    while len(order) < sum(len(g) for g in groups):
+        for g in groups:
+            if depth < len(g):
+                order.append(g[depth])
+        depth += 1
+    return order[:world]
+
+
+def gpu_map_for_run(world: int, local_rank: int, token: str, timeout_s: float = 90.0):
+    """The LOCAL_RANK -> GPU map of a `world`-process run on one box, agreed through a small file: local rank 0 measures the
+    uplink groups (only when fewer processes than GPUs run — otherwise the identity is the only map) and publishes the
+    map; the other ranks wait for it. Falls back to the identity map on any failure."""
+    import json
+    import time
+    import torch
+    ident = list(range(world))
+    n = torch.cuda.device_count()
+    if world <= 1 or world >= n:
+        return ident, None
+    path = os.path.join("/tmp", "ckb_gpu_map_%s_w%d.json" % (token, world))
+    t_start = time.time()          # a file left by an earlier run with the same token is older than this run: ignored
+    if local_rank == 0:
+        info = {"map": ident, "groups": None}
+        try:
+            groups, table = measure_uplink_groups(n)
+            info = {"map": spread_over_groups(world, groups), "groups": groups,
+                    "pair_gbs": {"%d-%d" % k: round(v, 1) for k, v in table.items()}}
+        except Exception as e:                                  # never let the probe take the run down
+            info["error"] = repr(e)
+        with open(path + ".tmp", "w") as f:
+            json.dump(info, f)
+        os.replace(path + ".tmp", path)
+        return info["map"], info
+    t0 = time.time()
+    while time.time() - t0 < timeout_s:
+        if os.path.exists(path) and os.path.getmtime(path) > t_start - 3.0:
+            try:
+                with open(path) as f:
+                    info = json.load(f)
+                return info["map"], info
+            except Exception:
+                pass
+        time.sleep(0.05)
+    return ident, None
