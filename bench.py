@@ -52,10 +52,12 @@ KMEANS_BYTES_PER_FRAME = 3 * N_FULL + 4 * N_FULL + 1083          # SURVEY.md 8(d
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (64 frames) from the `ncu --set full` captures under profiles/
 # (None = no capture of the current kernel yet)
 DRAM_TRAFFIC = {
-    "cnn_tc_front": 28010400 + 151286000,      # profiles/r1q_kernels_ncu_full_selected.csv
-    "ckb_warp_kernel": None,
-    "ckb_kmeans_cluster": None,
-    "ckb_mog2_kernel": None,
+    "cnn_tc_front": 28010400 + 151286000,         # profiles/r1q_kernels_ncu_full_selected.csv
+    "ckb_warp_kernel": 2 * (94518016 + 7100000),  # two 32-frame launches per step; profiles/r2_warp_ncu_full_selected.csv
+    # cluster kernel 27.75 MB (the 64 images, read once, nothing written) + zone vote 28.63 MB (reads them again);
+    # profiles/r2_stats_kernels_ncu_full_selected.csv
+    "ckb_kmeans_cluster": 27749376 + 28633088,
+    "ckb_mog2_kernel": 42328576 + 132352,         # the model state mostly stays in L2 between launches (same file)
 }
 SOFTMAX_TOLERANCE = ("CNN softmax vs the fp32 oracle: max_j |y_j - y_ref_j| / max_j y_ref_j <= 1e-3 per patch "
                      "(scale-relative, tests/test_gpu_cnn.py) with identical argmax; warp, k-means labels / centres, "
@@ -421,7 +423,7 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         prof = eng.profile_end() if profile else []
         return ms, prof, eng.launches - l0, sampler.finish(), out
 
-    def sustained(step, min_seconds=2.0, chunk=50):
+    def sustained(step, min_seconds=0.1 if args.quick else 2.0, chunk=10 if args.quick else 50):
         """the step back to back for at least `min_seconds` of device time (same on every rank: fixed step count
         derived from the burst timing would differ per rank, so ranks agree on the count through the chunk loop)"""
         barrier()
@@ -495,14 +497,14 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     # decoder sustains), (ii) an encoded 1080p file decoded on the host by several threads per rank.
     from camkifu_b200.video import FrameSource, RingClip, process_video
     vpipe = DetectPipeline(H, W, GSIZE, mode="neural", sub_batch=16, engine=eng)
-    vmem_frames = args.video_frames * world
+    vmem_frames = (256 if args.quick else args.video_frames) * world
     cores = os.cpu_count() or 1
     # decoder threads per rank: each owns a capture and seeks once; OpenCV's FFmpeg seek decodes ~16 frames at best and
     # for some frame numbers falls back to decoding from the start of the file (measured: 0.15 s .. 2 s per seek on this
     # 512-frame file, tools/_probe notes in DESIGN.md), so more than a few captures per rank cost more than they give
     decoders = max(1, min(4, cores // world - 1))
     vfile = os.path.join("/tmp", "ckb_bench_%s.avi" % os.environ.get("MASTER_PORT", "single"))
-    vfile_frames = 512
+    vfile_frames = 64 if args.quick else 512
     if rank == 0:
         import cv2
         wr = cv2.VideoWriter(vfile, cv2.VideoWriter_fourcc(*"MJPG"), 30, (W, H))
@@ -594,11 +596,11 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
 
     # ---- CPU baseline on this host (bounded samples; rank 0 of the N = 1 run only)
     threads = os.cpu_count() or 1
-    if world == 1:
+    if world == 1 and not args.quick:
         cpu_line = cpu_baseline_block(frames_np, mtx, params, video_file=vfile)
     else:
         cpu_line = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": "not timed at N > 1: see the N = 1 line and --impl reference"}
+                    "sample": "not timed at N > 1 (or with --quick): see the N = 1 line and --impl reference"}
 
     try:
         os.remove(vfile)
@@ -665,6 +667,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--video-frames", type=int, default=20480, help="frames per rank of the in-memory offline-video leg")
+    ap.add_argument("--quick", action="store_true", help="profiling runs (ncu): short sustained legs, small video legs, no CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
