@@ -63,21 +63,23 @@ def pick_gpus(world: int, levels=None):
     return chosen
 
 
-def measure_uplink_groups(n_gpus: int = None, mbytes: int = 64, reps: int = 4):
-    """Which GPUs share a host uplink, MEASURED: NVML reports every GPU pair of these boxes at the same PCIe level, yet
-    four ranks on GPUs 0-3 get the host -> device bandwidth of two links. For a reference GPU and each other GPU, copy
-    pinned host buffers to both at once: two GPUs behind one switch split one link's bandwidth (aggregate ~ 1 x a single
-    copy), two on separate links add up (~ 2 x). Returns (groups, table): groups = lists of GPU indices per uplink,
-    table = {(i, j): GB/s} of what was measured. Creates a CUDA context on every GPU: call from ONE process."""
+def measure_gpu_choice(world: int, n_gpus: int = None, mbytes: int = 64, reps: int = 4):
+    """Which `world` GPUs of the box to use, MEASURED. NVML reports every GPU pair of these boxes at the same PCIe level and
+    any TWO GPUs copy from the host at twice the rate of one (110 GB/s), yet four ranks on GPUs 0-3 together get 115 GB/s
+    while GPUs 0, 1, 4, 5 get 220: the GPUs hang off host bridges with a shared ceiling that only shows with three or
+    more streams. So the choice is greedy on the measured aggregate: start with GPU 0; add, one at a time, the GPU with
+    which all chosen GPUs together copy pinned host buffers fastest (ties within 5 % go to the lowest index). Returns
+    (gpus, log) with log = [(candidate set, GB/s)]. Creates a CUDA context on every GPU: call from ONE process."""
     import time
     import torch
     n = torch.cuda.device_count() if n_gpus is None else n_gpus
     nbytes = mbytes << 20
-    host = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    host = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(world)]
     dev = [torch.empty(nbytes, dtype=torch.uint8, device="cuda:%d" % g) for g in range(n)]
     streams = [torch.cuda.Stream(device="cuda:%d" % g) for g in range(n)]
 
     def run(gpus):
+        dt = 1.0
         for _ in range(2):                                   # warm-up, then timed
             for g in gpus:
                 torch.cuda.synchronize(g)
@@ -91,34 +93,23 @@ def measure_uplink_groups(n_gpus: int = None, mbytes: int = 64, reps: int = 4):
             dt = time.perf_counter() - t0
         return len(gpus) * reps * nbytes / dt / 1e9
 
-    table, groups, left = {}, [], list(range(n))
-    while left:
-        ref = left.pop(0)
-        single = table[(ref, ref)] = run([ref])
-        grp = [ref]
-        for g in list(left):
-            both = table[(ref, g)] = run([ref, g])
-            if both < 1.5 * single:
-                grp.append(g)
-                left.remove(g)
-        groups.append(grp)
-    return groups, table
-
-
-def spread_over_groups(world: int, groups):
-    """`world` GPUs, taken round-robin from the uplink groups (one from each before a second from any)."""
-    order, depth = [], 0
-    while len(order) < sum(len(g) for g in groups):
-        for g in groups:
-            if depth < len(g):
-                order.append(g[depth])
-        depth += 1
-    return order[:world]
+    chosen, log = [0], []
+    while len(chosen) < world:
+        best, best_bw = None, 0.0
+        for g in range(n):
+            if g in chosen:
+                continue
+            bw = run(chosen + [g])
+            log.append((chosen + [g], round(bw, 1)))
+            if bw > 1.05 * best_bw:
+                best, best_bw = g, bw
+        chosen.append(best)
+    return chosen, log
 
 
 def gpu_map_for_run(world: int, local_rank: int, token: str, timeout_s: float = 90.0):
-    """The LOCAL_RANK -> GPU map of a `world`-process run on one box, agreed through a small file: local rank 0 measures the
-    uplink groups (only when fewer processes than GPUs run — otherwise the identity is the only map) and publishes the
+    """The LOCAL_RANK -> GPU map of a `world`-process run on one box, agreed through a small file: local rank 0 measures
+    which GPUs to use (only when fewer processes than GPUs run — otherwise the identity is the only map) and publishes the
     map; the other ranks wait for it. Falls back to the identity map on any failure."""
     import json
     import time
@@ -130,11 +121,10 @@ def gpu_map_for_run(world: int, local_rank: int, token: str, timeout_s: float = 
     path = os.path.join("/tmp", "ckb_gpu_map_%s_w%d.json" % (token, world))
     t_start = time.time()          # a file left by an earlier run with the same token is older than this run: ignored
     if local_rank == 0:
-        info = {"map": ident, "groups": None}
+        info = {"map": ident}
         try:
-            groups, table = measure_uplink_groups(n)
-            info = {"map": spread_over_groups(world, groups), "groups": groups,
-                    "pair_gbs": {"%d-%d" % k: round(v, 1) for k, v in table.items()}}
+            gpus, log = measure_gpu_choice(world, n)
+            info = {"map": gpus, "measured_h2d_gbs": [["+".join(str(g) for g in c), bw] for c, bw in log]}
         except Exception as e:                                  # never let the probe take the run down
             info["error"] = repr(e)
         with open(path + ".tmp", "w") as f:
