@@ -501,8 +501,10 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     cores = os.cpu_count() or 1
     # decoder threads per rank: each owns a capture and seeks once; OpenCV's FFmpeg seek decodes ~16 frames at best and
     # for some frame numbers falls back to decoding from the start of the file (measured: 0.15 s .. 2 s per seek on this
-    # 512-frame file, tools/_probe notes in DESIGN.md), so more than a few captures per rank cost more than they give
-    decoders = max(1, min(4, cores // world - 1))
+    # 512-frame file, tools/_probe notes in DESIGN.md), so with
+    # several ranks reading one file more than a few captures per rank cost more than they give (8 / 7 per rank at 2 / 4
+    # ranks: 0.16 k frames/s; 3 per rank: 0.7 - 1.3 k)
+    decoders = max(1, min(8 if world == 1 else 3, cores // world - 1))
     vfile = os.path.join("/tmp", "ckb_bench_%s.avi" % os.environ.get("MASTER_PORT", "single"))
     vfile_frames = 64 if args.quick else 512
     if rank == 0:
@@ -538,6 +540,17 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         del fs
     barrier()
     vfile_s, vfile_n, vfile_mine = timed_video(vfile, decoders, 16)
+
+    # ---- per-rank step times and clocks of the headline leg (the max over ranks is what is reported; this shows whether a
+    # gap to N x the single-GPU value is one slow GPU or all of them)
+    mine_r = torch.tensor([ms_total / args.steps, float(clocks["sm_mhz"] or 0), float("sw_power_cap" in clocks["reasons"]),
+                           e2e_s * 1e3 / args.steps], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine_r) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine_r)
+    else:
+        per_rank = [mine_r]
+    per_rank = [[round(float(v), 4) for v in r] for r in per_rank]
 
     # ---- max over ranks
     t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s],
@@ -626,6 +639,8 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
                     "h2d_peak_gbs": h2d_peak, "h2d_frac": world * h2d * args.steps / e2e_s / 1e9 / h2d_peak,
                     "h2d_peak_how": "every rank copying a pinned 256 MB buffer 8 times at once, in this job"},
             "gather_ms": gather_ms,
+            "ranks": [{"gpu": gpu_map["map"][i] if i < len(gpu_map["map"]) else i, "ms_per_step": r[0], "sm_mhz": r[1],
+                       "sw_power_cap": bool(r[2]), "e2e_ms_per_step": r[3]} for i, r in enumerate(per_rank)],
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_line,
             "kernels": kernel_rows(agg, args.steps),

@@ -116,7 +116,10 @@ __device__ __forceinline__ uint8_t mog2_update(Mog2Px &s, const float d0, const 
     return background ? 0 : 255;
 }
 
-__global__ void __launch_bounds__(128) ckb_mog2_kernel(const uint8_t *__restrict__ img, int n, int npix, float *__restrict__ state,
+#ifndef MOG2_MINB
+#define MOG2_MINB 8      // resident CTAs per SM the register allocation is sized for (measured: see DESIGN.md)
+#endif
+__global__ void __launch_bounds__(128, MOG2_MINB) ckb_mog2_kernel(const uint8_t *__restrict__ img, int n, int npix, float *__restrict__ state,
                                                        const __grid_constant__ Mog2Rates rates, uint8_t *__restrict__ mask)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
