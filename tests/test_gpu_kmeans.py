@@ -166,3 +166,30 @@ def test_random_subregions_vs_oracle(engine, oracle):
             ref = oracle.c_find_stones(gob[t % 2], st, 19, rs, re, cs, ce)
         res = engine.find_stones(img, [st], rs, re, cs, ce, want=ALL)
         compare(res, 0, ref)
+
+
+def test_tiny_regions_and_odd_batches(engine, oracle):
+    """Clusters of 1 / 2 / 4 CTAs (regions of one to a few zones: the cluster size follows the pixel count), partial last
+    chunks, and batch sizes around the launch geometry (1, 3, 130 frames)."""
+    rng = np.random.default_rng(55)
+    frames, M, truth, _ = synth.make_clip(19, 3, 360, 480)
+    import cv2
+    gob = np.stack([cv2.warpPerspective(f, M, (380, 380)) for f in frames])
+    for t, (rs, re, cs, ce) in enumerate(((0, 1, 0, 1), (18, 19, 18, 19), (3, 4, 5, 8), (7, 9, 7, 9), (0, 3, 16, 19),
+                                          (10, 19, 0, 2), (0, 19, 18, 19))):
+        st = engine.L.ckb_rng_seed(700 + t)
+        res = engine.find_stones(torch.from_numpy(gob[t % 3:t % 3 + 1]).cuda(), [st], rs, re, cs, ce, want=ALL)
+        compare(res, 0, oracle.c_find_stones(gob[t % 3], st, 19, rs, re, cs, ce))
+    # batch sizes: the same three images repeated; every frame must equal the oracle's result for its own RNG state
+    for n in (1, 3, 130):
+        imgs = torch.from_numpy(gob[np.arange(n) % 3]).cuda()
+        states = [engine.L.ckb_rng_seed(900 + k % 5) for k in range(n)]
+        res = engine.find_stones(imgs, states, want=("stones", "trusted", "centers"))
+        refs = {}
+        for k in range(n):
+            key = (k % 3, k % 5)
+            if key not in refs:
+                refs[key] = oracle.c_find_stones(gob[k % 3], states[k])
+            assert np.array_equal(res["stones"][k].cpu().numpy(), refs[key]["stones"])
+            assert np.array_equal(res["centers"][k].cpu().numpy(), refs[key]["centers"])
+            assert bool(res["trusted"][k]) == refs[key]["trusted"]
