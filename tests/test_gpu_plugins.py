@@ -215,6 +215,17 @@ def test_process_video_file_sharded(tmp_path):
     # an in-memory array is a valid source too
     mem = process_video(frames, mtx, mode="neural", batch=16, engine=eng)
     assert np.array_equal(mem["stones"], whole["stones"])
+    # several decoder threads per rank: batches arrive out of order, the result does not change
+    multi = process_video(path, mtx, mode="both", batch=4, engine=eng, rng_state=st0, decoders=3)
+    for k in whole:
+        assert np.array_equal(multi[k], whole[k]), k
+    # a pinned ring standing for a long video (zero-copy source)
+    from camkifu_b200.video import RingClip
+    from camkifu_b200.pipeline import pinned_frames
+    ring = pinned_frames(8, H, W)
+    ring.copy_(torch.from_numpy(frames[:8]))
+    long = process_video(RingClip(ring, 29), mtx, mode="neural", batch=8, engine=eng)
+    assert np.array_equal(long["stones"], whole["stones"][np.arange(29) % 8])
 
 
 def test_sfclustering_keeps_a_background_model(golden):

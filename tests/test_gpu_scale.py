@@ -145,3 +145,39 @@ def test_config4_4k_mixed_board_sizes(oracle, gsize):
         assert np.array_equal(res["centers"][i].cpu().numpy(), ref["centers"])
         assert np.array_equal(res["stones"][i].cpu().numpy(), ref["stones"])
     assert np.array_equal(res["stones"].cpu().numpy(), truth)
+
+
+def test_pipeline_full_mode_stream_matches_oracle(engine, oracle):
+    """DetectPipeline(mode="full") — everything a finder runs per frame, statistics branch and CNN branch on two streams —
+    over three batches of a small 'game' clip: per-zone foreground counts equal the oracle's MOG2 (streamed across the
+    batches, the reference's learning-rate schedule), k-means board states equal the oracle's find_stones per frame, CNN
+    board states equal the single-stream engine call."""
+    from camkifu_b200 import synth, weights
+    from camkifu_b200.engine import rng_seed, rng_advance
+    from camkifu_b200.pipeline import DetectPipeline
+    import cv2
+    H, W, n = 240, 320, 60
+    frames, mtx, truth, _ = synth.make_game_clip(9, n, H, W, events=[(20, 1, 3, 4), (40, 2, 10, 12)])
+    engine.set_cnn_weights(weights.glorot_params(seed=0))
+    pipe = DetectPipeline(H, W, mode="full", sub_batch=8, engine=engine)
+    st0 = rng_seed(4)
+    got = {}
+    for b0 in range(0, n, 20):
+        res = pipe.detect(torch.from_numpy(frames[b0:b0 + 20]), mtx, rng_state=rng_advance(st0, b0))
+        for k, v in res.items():
+            got.setdefault(k, []).append(v.copy())
+    got = {k: np.concatenate(v) for k, v in got.items()}
+    model = oracle.CMog2((380, 380))
+    rects = oracle.c_zone_rects(19)
+    for i in range(n):
+        g = cv2.warpPerspective(frames[i], mtx, (380, 380))
+        fg = model.apply(g, 0.01 if i < 50 else 0.005)
+        counts = np.array([[int(fg[a0:a1, b0:b1].sum()) // 255 for (a0, b0, a1, b1) in rects[r]] for r in range(19)])
+        assert np.array_equal(got["fg_counts"][i], counts), "frame %d" % i
+        if i % 7 == 0:
+            ref = oracle.c_find_stones(g, rng_advance(st0, i))
+            assert np.array_equal(got["km_stones"][i], ref["stones"]) and bool(got["km_trusted"][i]) == ref["trusted"]
+    gob = engine.warp(torch.from_numpy(frames[:20]).cuda(), mtx)
+    nn = engine.cnn_forward(gob, want_softmax=False)
+    assert np.array_equal(got["stones"][:20], nn["stones"].cpu().numpy())
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0 and pipe.frames_seen == n
