@@ -437,7 +437,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     KC_TICK(1);   // first cluster barrier (cluster start-up skew)
 
     // ---- k-means++ seeding (the three attempts side by side)
+#ifdef KC_TIMING
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp_prev = clock64();
+#define KC_PTICK(slot) do { const long long t_now = clock64(); tp[slot] += t_now - tp_prev; tp_prev = t_now; } while (0)
+#else
+#define KC_PTICK(slot) do { } while (0)
+#endif
     pp_pass_cluster<NW>(cluster, sh, pix, cxx, seg, cpc, nch, ch_lo, N, 0, 1, 0, rank, C, warp, swarp, lane);
+    KC_PTICK(0);
     if (tid < 3) sh.cenw[tid][0] = sh.candw[tid][0];
     for (int e = tid; e < 3 * nch; e += NT) {
         const int a = e / nch, lc = e - a * nch;
@@ -445,10 +453,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     }
     __syncthreads();
     for (int k = 1; k < (KC_EXP == 4 ? 1 : 3); k++) {
+        KC_PTICK(1);
         pp_sample_cluster(cluster, sh, pix, seg, cpc, nch, ch_lo, N, k, k - 1, C, rank, k - 1, swarp, lane);
+        KC_PTICK(2);
         if (tid < 9) sh.candw[tid / 3][tid % 3] = region_px(img, S, rg, sh.cand_idx[k - 1][tid / 3][tid % 3]);
         __syncthreads();
+        KC_PTICK(3);
         pp_pass_cluster<NW>(cluster, sh, pix, cxx, seg, cpc, nch, ch_lo, N, k, 3, k, rank, C, warp, swarp, lane);
+        KC_PTICK(4);
         if (tid < 3) {
             // best trial: strict '<' in trial order
             const int a = tid;
@@ -837,6 +849,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
     }
     KC_TICK(8);   // compactness
 #ifdef KC_TIMING
+    if (tid == 0 && unit == (gridDim.x / C > 50 ? 50 : 0))
+        printf("rank %d pp: passA %lld  copy %lld  sample %lld  fetch %lld  passBC %lld\n", rank, tp[0], tp[1], tp[2], tp[3], tp[4]);
     if (tid == 0 && unit == (gridDim.x / C > 50 ? 50 : 0))
         printf("rank %d iters %d %d %d: load %lld  sync0 %lld  pp %lld  pass %lld  wait %lld  xchg %lld  tail %lld (search %lld sweep %lld wait %lld)  centres %lld  compact %lld  total %lld\n",
                rank, sh.iters[0], sh.iters[1], sh.iters[2], tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[9], tk[10], tk[11], tk[7], tk[8], clock64() - t_begin);

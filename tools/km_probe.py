@@ -44,7 +44,7 @@ frames, mtx, truth, _ = synth.make_clip_parallel(1000, 64, 1080, 1920)
 goban = eng.warp(torch.from_numpy(frames).cuda(), mtx)
 states = rng_states(rng_seed(0), 0, 64)
 n = 64
-for rep in range(1 if timing else 3):
+for rep in range(3):
     eng.profile_begin(256)
     res = eng.find_stones(goban[:n], states[:n])
     torch.cuda.synchronize()
