@@ -400,6 +400,39 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1) / 5
 
+    def graphed(step_fn, label):
+        """The step as CUDA graphs (one per resident batch), replayed: the timed loops then depend on the GPU only, not on
+        how fast this process issues ~10-17 launches per step next to 7 other ranks. Falls back to eager launches if the
+        capture fails. Returns (callable(i) -> outputs, launches per step, captured?)."""
+        l0 = eng.launches
+        step_fn(0)
+        per_step = eng.launches - l0
+        try:
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                for i in range(2):
+                    step_fn(i)
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize()
+            graphs, outs = [], []
+            for v in range(n_rot):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    o = step_fn(v)
+                graphs.append(g)
+                outs.append(o)
+            torch.cuda.synchronize()
+
+            def replay(i):
+                graphs[i % n_rot].replay()
+                return outs[i % n_rot]
+            return replay, per_step, True
+        except Exception as e:       # noqa: BLE001 - any capture problem: time the eager step instead, and say so
+            sys.stderr.write("bench: CUDA graph capture of the %s step failed (%r); timing eager launches\n" % (label, e))
+            torch.cuda.synchronize()
+            return step_fn, per_step, False
+
     def timed_steps(step, steps, warmup, profile=True, gather=False):
         for i in range(warmup):
             step(i)
@@ -446,14 +479,21 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         barrier()
         return e0.elapsed_time(e1), n, sampler.finish()
 
+    full_state["frames"] = 2 * BATCH          # steady state of the background model (learning rate 0.005) for the graphs
+    g_neural, lps_neural, cap_neural = graphed(step_neural, "SfNeural")
+    g_full, lps_full, cap_full = graphed(step_full, "pipeline")
     # ---- leg A: headline (config 2), burst over K steps
-    ms_total, prof, launches, clocks, out = timed_steps(step_neural, args.steps, args.warmup, gather=True)
+    ms_total, _, _, clocks, out = timed_steps(g_neural, args.steps, args.warmup, profile=False, gather=True)
+    launches = lps_neural * args.steps
+    # the same step with eager launches and an event after every kernel: per-kernel times for the roofline
+    nser_ms, prof, _, _, _ = timed_steps(step_neural, args.steps, 1)
     # ---- leg C: the whole pipeline (config 3), burst (before the sustained legs, which leave the GPU power-capped)
-    pipe_ms, _, pipe_launches, pipe_clocks, pipe_out = timed_steps(step_full, args.steps, args.warmup, profile=False)
+    pipe_ms, _, _, pipe_clocks, pipe_out = timed_steps(g_full, args.steps, args.warmup, profile=False)
+    pipe_launches = lps_full * args.steps
     pser_ms, pipe_prof, _, _, _ = timed_steps(step_full_serial, args.steps, 1)       # one stream: per-kernel times
     # ---- legs B / D: both steps sustained
-    sus_ms, sus_n, sus_clocks = sustained(step_neural)
-    psus_ms, psus_n, psus_clocks = sustained(step_full)
+    sus_ms, sus_n, sus_clocks = sustained(g_neural)
+    psus_ms, psus_n, psus_clocks = sustained(g_full)
 
     # ---- host -> device ceiling of this job: every rank copies a pinned 256 MB buffer at the same time
     hb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
@@ -489,8 +529,9 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     e2e_s, h2d, d2h, res = e2e("neural", 16)
     e2e_ok = bool(np.array_equal(res["stones"], step_neural(0)["stones"].cpu().numpy()))
     pe2e_s, ph2d, pd2h, pres = e2e("full", 64)
-    pe2e_ok = bool(np.array_equal(pres["km_stones"], pipe_out[1]["stones"].cpu().numpy()) and
-                   np.array_equal(pres["stones"], pipe_out[0]["stones"].cpu().numpy()))
+    ref_nn, ref_km, _ = step_full_serial(0)                   # the resident path on the same 64 frames, eager
+    pe2e_ok = bool(np.array_equal(pres["km_stones"], ref_km["stones"].cpu().numpy()) and
+                   np.array_equal(pres["stones"], ref_nn["stones"].cpu().numpy()))
 
     # ---- offline video (BASELINE.json configs[4]): process_video = decode -> pinned ring -> detect_stream, the frames
     # of one video sharded over the ranks, one final gather. (i) a long clip held in host memory (what the path behind the
@@ -627,6 +668,9 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
             "config": {"workload": WORKLOAD, "frame": [H, W], "gsize": GSIZE, "frames_per_step_per_gpu": BATCH,
                        "weights": "glorot_uniform seed 0 (reference architecture, nn_manager.py:277-298)",
                        "l2": "inputs larger than L2: two resident 398 MB batches used alternately",
+                       "launch": ("CUDA graphs (one per resident batch) replayed" if cap_neural else "eager launches") +
+                                 "; per-kernel times from a separate eager run of the same step with an event after every "
+                                 "kernel (%.3f ms per step)" % (nser_ms / args.steps),
                        "parallelism": "frames sharded across %d GPU(s), final all_gather of board states" % world,
                        "gpu_map": gpu_map, "numa_bound": numa_bound, "cpus_available_to_rank0": len(os.sched_getaffinity(0)),
                        "tolerance": SOFTMAX_TOLERANCE},
@@ -647,6 +691,7 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
             "cnn": {"tflops_algorithmic": cnn_flop / (cnn_ms * 1e-3) / 1e12, "ms_per_step": cnn_ms},
             "pipeline": {"workload": PIPE_WORKLOAD, "value": fps(args.steps, pipe_ms), "unit": UNIT,
                          "ms_per_step": pipe_ms / args.steps, "gpu_launches": pipe_launches, "clocks": pipe_clocks,
+                         "launch": "CUDA graphs replayed" if cap_full else "eager launches",
                          "streams": "two: background model + running average + k-means next to the CNN (both read the warped "
                                     "images); `kernels` below are timed in a separate single-stream run (%.3f ms per step)"
                                     % (pser_ms / args.steps),
