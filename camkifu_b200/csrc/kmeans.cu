@@ -20,12 +20,19 @@
 // to SfClustering's float32 running average) the sums are integers that float32 represents exactly below 2^24, so
 // the serial walk is only needed in the chunk where a running sum passes 2^24 (beyond it, up to 2^25, the rounding
 // is a two-state parity automaton that is evaluated in parallel) — see the Lloyd loop.
-// Throughput comes from running many (frame, attempt) CTAs side by side: grid = 3 attempts x n frames, 256 threads.
+// Throughput comes from running many (frame, attempt) CTAs side by side: grid = 3 attempts x n frames.
 //
-// Kernels:  ckb_pack_region_*   region pixels -> linear, vector-loadable scratch (uchar4 / float4 per pixel)
+// Since round 2 the uint8 path is kmeans_cluster.cu (one thread-block cluster per frame, pixels resident in distributed
+// shared memory); the kernel below serves float32 images (SfClustering's running average) and the attempts the cluster
+// kernel declines (KM_ITERS_FALLBACK: an empty cluster, sums within reach of 2^25), for which it is launched after it and
+// exits at once otherwise.
+//
+// Kernels:  ckb_pack_region     region pixels -> linear, vector-loadable scratch (uchar4 / float4 per pixel)
 //           ckb_kmeans_attempt  one CTA per (frame, attempt)
-//           ckb_zone_classify   one CTA per frame: best attempt, labels, zone histograms (warp per zone, ballot/popc
-//                               reductions), ratios, stones, density check
+//           ckb_zone_classify   12 CTAs per (frame, region): best attempt, labels of each zone's disk read from the image
+//                               in place, zone histograms (warp per zone), ratios, stones; the last CTA of a unit
+//                               (ticket) runs the density check
+// Launchers: ckb_find_stones (one region) and ckb_find_stones_regions (SfMeta's 3 x 3 regions x n frames at once).
 #include "kmeans_common.cuh"
 
 #define KM_THREADS_F32 256             // float32 input: the serial centre sums dominate, many small CTAs per SM
