@@ -742,6 +742,9 @@ def main():
     token = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
     gpu_map, map_info = gpu_map_for_run(world, local_rank, token) if world > 1 else ([local_rank], None)
     gpu_index = gpu_map[local_rank] if local_rank < len(gpu_map) else local_rank
+    import torch
+    if gpu_index >= torch.cuda.device_count() > 0:      # a launcher that shows each rank its own GPU only
+        gpu_index = local_rank % torch.cuda.device_count()
     if world > 1:
         import torch
         import torch.distributed as dist
