@@ -146,34 +146,55 @@ __device__ __forceinline__ long long warp_incl_scan_ll(long long v, int lane)
     return v;
 }
 
-// Labels of four pixels against the centres `oc` (first minimum of the float32 distances): k0[q] / k1[q] = pixel q belongs
-// to cluster 0 / 1 (neither: cluster 2). `valid` has bit q set for pixels inside the region. Warp-collective.
-__device__ __forceinline__ void classify4(const uint32_t p[4], unsigned valid, const KcFilter &F, const float *oc,
-                                          bool k0[4], bool k1[4])
+// One 128-pixel chunk of a Lloyd pass for one attempt: labels of this lane's 4 pixels against the centres `oc` (filter, or
+// the exact float32 chain for the whole warp if any pixel is undecided), packed sums of clusters 0 and 1 (x | y << 16,
+// z | count << 16) reduced over the warp, and the label written back into the pixel word's spare byte (2 bits per
+// attempt: the tail and the compactness pass read it back). FULL: every pixel of the chunk is inside the region (all
+// chunks but the region's last), so no validity masks. Classification and accumulation are one loop, so that no
+// predicate outlives its pixel.
+template <bool FULL>
+__device__ __forceinline__ uint4 lloyd_chunk(uint4 *slot, unsigned valid, const KcFilter &F, const float *oc, int lsh)
 {
+    const uint4 v = *slot;
+    const uint32_t p[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t keep = ~(3u << lsh), l1 = 1u << lsh, l2 = 2u << lsh;
+    uint32_t a0 = 0u, b0 = 0u, a1 = 0u, b1 = 0u, pl[4];
     bool unsure = false;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int f01 = dp4a_uu(p[q], F.lo[0], F.k[0]) + (dp4a_us(p[q], F.hi[0], 0) * 256);
+        const int f01 = dp4a_uu(p[q], F.lo[0], F.k[0]) + dp4a_us(p[q], F.hi[0], 0) * 256;
         const int f02 = dp4a_uu(p[q], F.lo[1], F.k[1]) + dp4a_us(p[q], F.hi[1], 0) * 256;
         const int f12 = dp4a_uu(p[q], F.lo[2], F.k[2]) + dp4a_us(p[q], F.hi[2], 0) * 256;
         const bool a = f01 < -KC_T && f02 < -KC_T;
         const bool b = f01 > KC_T && f12 < -KC_T;
         const bool c = f02 > KC_T && f12 > KC_T;
-        const bool v = (valid >> q) & 1u;
-        k0[q] = a && v;
-        k1[q] = b && v;
-        unsure |= v && !(a || b || c);
+        const bool vq = FULL || ((valid >> q) & 1u);
+        const uint32_t pa = __byte_perm(p[q], 0u, 0x4140);       // x | y << 16
+        const uint32_t pb = __byte_perm(p[q], 0x100u, 0x4542);   // z | 1 << 16
+        if (a && vq) { a0 += pa; b0 += pb; }
+        if (b && vq) { a1 += pa; b1 += pb; }
+        pl[q] = (p[q] & keep) | (a ? 0u : (b ? l1 : l2));
+        unsure |= vq && !(a || b || c);
     }
     if (__any_sync(0xffffffffu, unsure)) {
+        a0 = b0 = a1 = b1 = 0u;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int lab = argmin3(unpack_px(p[q]), oc);
-            const bool v = (valid >> q) & 1u;
-            k0[q] = v && lab == 0;
-            k1[q] = v && lab == 1;
+            const bool vq = FULL || ((valid >> q) & 1u);
+            const uint32_t pa = __byte_perm(p[q], 0u, 0x4140);
+            const uint32_t pb = __byte_perm(p[q], 0x100u, 0x4542);
+            if (vq && lab == 0) { a0 += pa; b0 += pb; }
+            if (vq && lab == 1) { a1 += pa; b1 += pb; }
+            pl[q] = (p[q] & keep) | ((uint32_t)lab << lsh);
         }
     }
+    *slot = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    a0 = __reduce_add_sync(0xffffffffu, a0);
+    b0 = __reduce_add_sync(0xffffffffu, b0);
+    a1 = __reduce_add_sync(0xffffffffu, a1);
+    b1 = __reduce_add_sync(0xffffffffu, b1);
+    return make_uint4(a0, b0, a1, b1);
 }
 
 // chunk sum of chain c = 3 k + j (cluster k, channel j) from the packed per-chunk reductions
@@ -210,19 +231,21 @@ __device__ __forceinline__ void pp_pass_attempt(const KcShared &sh, int a, const
     for (int lc = warp; lc < nch; lc += NW) {
         const uint4 v = ((const uint4 *)pix)[lc * 32 + lane];
         const uint32_t p[4] = {v.x, v.y, v.z, v.w};
-        const int rem = N - ((ch_lo + lc) * KC_CH + lane * 4);
+        // pixels of the region this lane holds in the chunk: 4, except in the region's last chunk
+        const int rem = (ch_lo + lc + 1) * KC_CH <= N ? 4 : N - ((ch_lo + lc) * KC_CH + lane * 4);
         int acc[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (q < rem) {
-                // distances relative to |x|^2, which is added per chunk (cxx): d' = |c|^2 - 2 x.c
-                int base = 0x7fffffff;
-                if (ncen > 0) base = bc[0] - 2 * dp4a_uu(p[q], bw[0], 0);
-                if (ncen > 1) base = min(base, bc[1] - 2 * dp4a_uu(p[q], bw[1], 0));
+            // distances relative to |x|^2, which is added per chunk (cxx): d' = |c|^2 - 2 x.c
+            int base = 0x7fffffff;
+            if (ncen > 0) base = bc[0] - 2 * dp4a_uu(p[q], bw[0], 0);
+            if (ncen > 1) base = min(base, bc[1] - 2 * dp4a_uu(p[q], bw[1], 0));
 #pragma unroll
-                for (int t = 0; t < 3; t++)
-                    if (t < ncand) acc[t] += min(cc[t] - 2 * dp4a_uu(p[q], cw[t], 0), base);
-            }
+            for (int t = 0; t < 3; t++)
+                if (t < ncand) {
+                    const int m = min(cc[t] - 2 * dp4a_uu(p[q], cw[t], 0), base);
+                    acc[t] += q < rem ? m : 0;
+                }
         }
 #pragma unroll
         for (int t = 0; t < 3; t++) {
@@ -523,31 +546,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
             const int lsh = 24 + 2 * a;
             uint4 *csum_a = csum + a * cpc;
             for (int lc = warp; lc < nch; lc += NW) {
-                const uint4 v = ((const uint4 *)pix)[lc * 32 + lane];
-                const uint32_t p[4] = {v.x, v.y, v.z, v.w};
-                const int rem = N - ((ch_lo + lc) * KC_CH + lane * 4);
-                const unsigned valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-                bool k0[4], k1[4];
-                classify4(p, valid, F, oc, k0, k1);
-                uint32_t a0 = 0u, b0 = 0u, a1 = 0u, b1 = 0u;
-                uint32_t pl[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t pa = __byte_perm(p[q], 0u, 0x4140);       // x | y << 16
-                    const uint32_t pb = __byte_perm(p[q], 0x100u, 0x4542);   // z | 1 << 16
-                    if (k0[q]) { a0 += pa; b0 += pb; }
-                    if (k1[q]) { a1 += pa; b1 += pb; }
-                    // the label goes into the pixel word's spare byte (2 bits per attempt): the tail and the compactness
-                    // pass read it back instead of classifying again
-                    const uint32_t lab = k0[q] ? 0u : (k1[q] ? 1u : 2u);
-                    pl[q] = (p[q] & ~(3u << lsh)) | (lab << lsh);
+                uint4 *slot = (uint4 *)pix + lc * 32 + lane;
+                uint4 sums;
+                if ((ch_lo + lc + 1) * KC_CH <= N) {
+                    sums = lloyd_chunk<true>(slot, 0xfu, F, oc, lsh);
+                } else {
+                    const int rem = N - ((ch_lo + lc) * KC_CH + lane * 4);
+                    sums = lloyd_chunk<false>(slot, rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u)), F, oc, lsh);
                 }
-                ((uint4 *)pix)[lc * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                a0 = __reduce_add_sync(0xffffffffu, a0);
-                b0 = __reduce_add_sync(0xffffffffu, b0);
-                a1 = __reduce_add_sync(0xffffffffu, a1);
-                b1 = __reduce_add_sync(0xffffffffu, b1);
-                if (lane == 0) csum_a[lc] = make_uint4(a0, b0, a1, b1);
+                if (lane == 0) csum_a[lc] = sums;
             }
         }
         KC_TICK(3);   // Lloyd pass (this warp's chunks)
