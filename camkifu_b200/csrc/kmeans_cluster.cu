@@ -234,18 +234,27 @@ __device__ __forceinline__ void pp_pass_attempt(const KcShared &sh, int a, const
         // pixels of the region this lane holds in the chunk: 4, except in the region's last chunk
         const int rem = (ch_lo + lc + 1) * KC_CH <= N ? 4 : N - ((ch_lo + lc) * KC_CH + lane * 4);
         int acc[3] = {0, 0, 0};
+        // distances relative to |x|^2, which is added per chunk (cxx): d' = |c|^2 - 2 x.c
+        if (rem >= 4) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            // distances relative to |x|^2, which is added per chunk (cxx): d' = |c|^2 - 2 x.c
-            int base = 0x7fffffff;
-            if (ncen > 0) base = bc[0] - 2 * dp4a_uu(p[q], bw[0], 0);
-            if (ncen > 1) base = min(base, bc[1] - 2 * dp4a_uu(p[q], bw[1], 0));
+            for (int q = 0; q < 4; q++) {
+                int base = 0x7fffffff;
+                if (ncen > 0) base = bc[0] - 2 * dp4a_uu(p[q], bw[0], 0);
+                if (ncen > 1) base = min(base, bc[1] - 2 * dp4a_uu(p[q], bw[1], 0));
 #pragma unroll
-            for (int t = 0; t < 3; t++)
-                if (t < ncand) {
-                    const int m = min(cc[t] - 2 * dp4a_uu(p[q], cw[t], 0), base);
-                    acc[t] += q < rem ? m : 0;
-                }
+                for (int t = 0; t < 3; t++)
+                    if (t < ncand) acc[t] += min(cc[t] - 2 * dp4a_uu(p[q], cw[t], 0), base);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int base = 0x7fffffff;
+                if (ncen > 0) base = bc[0] - 2 * dp4a_uu(p[q], bw[0], 0);
+                if (ncen > 1) base = min(base, bc[1] - 2 * dp4a_uu(p[q], bw[1], 0));
+#pragma unroll
+                for (int t = 0; t < 3; t++)
+                    if (t < ncand && q < rem) acc[t] += min(cc[t] - 2 * dp4a_uu(p[q], cw[t], 0), base);
+            }
         }
 #pragma unroll
         for (int t = 0; t < 3; t++) {
@@ -813,12 +822,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) ckb_kmeans_cluster_u8(const uin
         for (int lc = warp; lc < nch; lc += NW) {
             const uint4 v = ((const uint4 *)pix)[lc * 32 + lane];
             const uint32_t p[4] = {v.x, v.y, v.z, v.w};
-            const int rem = N - ((ch_lo + lc) * KC_CH + lane * 4);
-            const unsigned valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+            const int rem = (ch_lo + lc + 1) * KC_CH <= N ? 4 : N - ((ch_lo + lc) * KC_CH + lane * 4);
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if ((valid >> q) & 1u) {
+                if (q < rem) {
                     const float3 x = unpack_px(p[q]);
                     const uint32_t lab = (p[q] >> lsh) & 3u;      // assigned against oldc by the attempt's last pass
                     const float cx = lab == 0u ? nc[0] : (lab == 1u ? nc[3] : nc[6]);
