@@ -583,6 +583,29 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         del fs
     barrier()
     vfile_s, vfile_n, vfile_mine = timed_video(vfile, decoders, 16)
+    # (iii) the same file decoded on the device: the compressed frames cross PCIe, nvJPEG decodes 256-frame batches into
+    # the buffer the warp reads (csrc/jpeg_ingest.cu). The file's frames repeated to 512 per rank: nvJPEG's GPU Huffman
+    # path needs batches of more than 100 frames.
+    from camkifu_b200.video import MjpegAvi
+    vj = None
+    if not args.quick:
+        try:
+            long_avi = MjpegAvi(vfile).repeat(max(1, 512 * world // vfile_frames))
+
+            def timed_nvjpeg():
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record()
+                o = process_video(long_avi, mtx, mode="neural", batch=256, pipeline=vpipe, decoders=2, ingest="nvjpeg")
+                v1.record()
+                barrier()
+                return v0.elapsed_time(v1) / 1e3, o["stones"].shape[0]
+            timed_nvjpeg()                      # page-locks / allocates the decoder's buffers
+            vj_s, vj_n = timed_nvjpeg()
+            vj = {"seconds": vj_s, "frames": vj_n, "backend": eng.jpeg_backend(),
+                  "mb_per_frame": float(long_avi.sizes.mean()) / 1e6}
+        except Exception as e:       # noqa: BLE001 - an optional leg: report why it is missing
+            vj = {"error": repr(e)}
+            barrier()
 
     # ---- per-rank step times and clocks of the headline leg (the max over ranks is what is reported; this shows whether a
     # gap to N x the single-GPU value is one slow GPU or all of them)
@@ -596,11 +619,13 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     per_rank = [[round(float(v), 4) for v in r] for r in per_rank]
 
     # ---- max over ranks
-    t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s,
+                      vj["seconds"] if vj and "seconds" in vj else -1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s = (float(v) for v in t)
+    ms_total, e2e_s, sus_ms, pipe_ms, psus_ms, pe2e_s, h2d_ms, vmem_s, vfile_s, vdec_s, vj_max = (float(v) for v in t)
+    if vj and "seconds" in vj:
+        vj["seconds"] = vj_max
     if rank != 0:
         return
 
@@ -717,7 +742,14 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
                                "source": "MJPG 1080p .avi written by rank 0 (%d frames), OpenCV/FFmpeg decode on the host, "
                                          "%d decoder threads per rank straight into pinned slots" % (vfile_frames, decoders),
                                "decode_only_fps": vfile_n / vdec_s, "host_cores": cores,
-                               "limiter": "host decode" if vfile_n / vdec_s < 0.8 * vmem_n / vmem_s else "host -> device copies"}},
+                               "limiter": "host decode" if vfile_n / vdec_s < 0.8 * vmem_n / vmem_s else "host -> device copies"},
+                      "file_nvjpeg": ({"value": vj["frames"] / vj["seconds"], "unit": UNIT, "frames": vj["frames"],
+                                       "seconds": vj["seconds"], "backend": vj["backend"],
+                                       "source": "the same MJPG frames (%.2f MB each) looped to %d frames, decoded on the device "
+                                                 "in 256-frame batches (process_video(ingest='nvjpeg')): compressed frames cross "
+                                                 "PCIe; pixels differ from the host decoder's by <= 3 levels, k-means board states "
+                                                 "identical (tools/nvjpeg_probe.py, tests)" % (vj["mb_per_frame"], vj["frames"]),
+                                       "limiter": "nvJPEG decode on the GPU"} if vj and "seconds" in vj else vj)},
             "parity_check": check}
     print(json.dumps(line), flush=True)
 

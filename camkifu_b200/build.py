@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcamkifu_b200.so")
-SOURCES = ["ckb_api.cu", "geometry.cu", "warp.cu", "mog2.cu", "kmeans.cu", "kmeans_cluster.cu", "zones.cu", "cnn_pack.cu", "cnn_simt.cu", "cnn_tc.cu", "cnn_tc_front.cu"]
+SOURCES = ["ckb_api.cu", "geometry.cu", "warp.cu", "mog2.cu", "kmeans.cu", "kmeans_cluster.cu", "zones.cu", "jpeg_ingest.cu", "cnn_pack.cu", "cnn_simt.cu", "cnn_tc.cu", "cnn_tc_front.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
             print(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-    subprocess.run([nvcc(), "-shared", "-o", out] + objs + ["-lcudart"], check=True)
+    subprocess.run([nvcc(), "-shared", "-o", out] + objs + ["-lcudart", "-ldl"], check=True)
     return out
 
 

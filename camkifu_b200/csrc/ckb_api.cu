@@ -8,6 +8,7 @@
 
 int ckb_kmeans_init_tables(ckb_ctx *ctx);
 void ckb_cnn_free(ckb_ctx *ctx);
+void ckb_jpeg_free(ckb_ctx *ctx);
 
 extern "C" int ckb_version(void) { return CKB_VERSION; }
 
@@ -208,6 +209,7 @@ extern "C" int ckb_destroy(ckb_ctx *ctx)
     if (!ctx) return CKB_E_INVALID;
     cudaSetDevice(ctx->device);
     ckb_cnn_free(ctx);
+    ckb_jpeg_free(ctx);
     if (ctx->d_rects) cudaFree(ctx->d_rects);
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     for (int i = 0; i < ctx->prof_cap; i++)

@@ -12,6 +12,7 @@
 #define CKB_MAX_ZONES (CKB_MAX_G * CKB_MAX_G)
 
 struct ckb_cnn_weights;  // cnn_pack.cu
+struct ckb_jpeg_state;   // jpeg_ingest.cu
 
 struct ckb_prof_entry {
     const char *name;   // NULL = boundary marker (entry of an API call)
@@ -30,6 +31,7 @@ struct ckb_ctx {
     uint8_t *d_mask;    // [S*S] disk mask
     int32_t h_rects[CKB_MAX_ZONES * 4];
     ckb_cnn_weights *cnn;
+    struct ckb_jpeg_state *jpeg;   // nvJPEG handles of the Motion-JPEG ingest (jpeg_ingest.cu), created on first use
     // per-kernel timing (ckb_profile_begin / ckb_profile_end): one CUDA event after every launch on the caller's stream
     cudaStream_t cur_stream;
     int prof_on, prof_n, prof_cap;

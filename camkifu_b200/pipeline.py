@@ -93,14 +93,15 @@ class DetectPipeline:
         stay untouched until the batch is collected; at most DEPTH batches may be outstanding."""
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
-        n = frames.shape[0]
+        on_device = frames.is_cuda      # frames already in HBM (e.g. decoded there): no upload, the warp reads them in place;
+        n = frames.shape[0]             # whatever produced them must have been enqueued on comp_stream
         assert tuple(frames.shape[1:]) == (self.H, self.W, 3)
         ticket = self._ticket
         self._ticket += 1
         sl = self._slot(ticket, n)
         out = sl["out"]
         eng = self.eng
-        roi = eng.frame_roi(mtx, self.H, self.W) if crop else None
+        roi = eng.frame_roi(mtx, self.H, self.W) if (crop and not on_device) else None
         st0 = rng_seed(0) if rng_state is None else rng_state
         if self.mode != "neural":
             sl["h_states"][:n].copy_(torch.from_numpy(np.asarray(rng_states(st0, 0, n), dtype=np.uint64).astype(np.int64)))
@@ -114,14 +115,18 @@ class DetectPipeline:
             k = self._k
             self._k += 1
             b = k & 1
-            with torch.cuda.stream(self.copy_stream):
-                if k >= 2:
-                    self.copy_stream.wait_event(self.ev_free[b])
-                self.h2d_bytes += eng.upload_frames(frames[f0:f0 + m], self.d_frames[b], roi)
-                self.ev_up[b].record(self.copy_stream)
+            if not on_device:
+                with torch.cuda.stream(self.copy_stream):
+                    if k >= 2:
+                        self.copy_stream.wait_event(self.ev_free[b])
+                    self.h2d_bytes += eng.upload_frames(frames[f0:f0 + m], self.d_frames[b], roi)
+                    self.ev_up[b].record(self.copy_stream)
             with torch.cuda.stream(self.comp_stream):
-                self.comp_stream.wait_event(self.ev_up[b])
-                goban = eng.warp(self.d_frames[b][:m], mtx, out=self.d_goban[:m])
+                if on_device:
+                    goban = eng.warp(frames[f0:f0 + m], mtx, out=self.d_goban[:m])
+                else:
+                    self.comp_stream.wait_event(self.ev_up[b])
+                    goban = eng.warp(self.d_frames[b][:m], mtx, out=self.d_goban[:m])
                 self.ev_free[b].record(self.comp_stream)
                 # the statistics branch (background model, running average, k-means) and the CNN branch both only read
                 # the warped images: in mode "full" the first runs on a side stream next to the second

@@ -69,6 +69,71 @@ class RingClip:
         return self.ring[a:a + m], m
 
 
+class MjpegAvi:
+    """Index of a Motion-JPEG AVI: where each frame's JPEG sits in the (memory-mapped) file. RIFF walk: the video chunks
+    ('..dc' / '..db') of every 'movi' list ('rec ' groups and OpenDML 'AVIX' segments included). Raises ValueError if the
+    file is not an AVI whose first video chunk is a JPEG — other containers / codecs go through FrameSource."""
+
+    def __init__(self, path: str):
+        import struct
+        self.path = path
+        self.data = np.memmap(path, dtype=np.uint8, mode="r")
+        buf = self.data
+        size = buf.shape[0]
+        if size < 12 or bytes(buf[0:4]) != b"RIFF" or bytes(buf[8:12]) != b"AVI ":
+            raise ValueError(path + " is not an AVI file")
+        offs, lens = [], []
+
+        def walk(pos, end):
+            while pos + 8 <= end:
+                cc = bytes(buf[pos:pos + 4])
+                ln = struct.unpack("<I", bytes(buf[pos + 4:pos + 8]))[0]
+                body = pos + 8
+                if cc in (b"RIFF", b"LIST"):
+                    kind = bytes(buf[body:body + 4])
+                    if cc == b"RIFF" or kind in (b"movi", b"rec "):
+                        walk(body + 4, min(end, body + ln))
+                elif cc[2:4] in (b"dc", b"db") and ln > 0:
+                    offs.append(body)
+                    lens.append(ln)
+                pos = body + ln + (ln & 1)
+
+        walk(0, size)
+        if not offs or bytes(buf[offs[0]:offs[0] + 2]) != b"\xff\xd8":
+            raise ValueError(path + " holds no Motion-JPEG video chunks")
+        self.offsets = np.asarray(offs, dtype=np.int64)
+        self.sizes = np.asarray(lens, dtype=np.int64)
+        self.base_address = int(self.data.ctypes.data)
+        self.H, self.W = self._frame_size(bytes(buf[offs[0]:offs[0] + min(lens[0], 65536)]))
+
+    @staticmethod
+    def _frame_size(jpeg: bytes):
+        """(height, width) from the frame header (SOF0 / SOF1 / SOF2 marker) of a JPEG."""
+        i = 2
+        while i + 9 < len(jpeg):
+            if jpeg[i] != 0xFF:
+                i += 1
+                continue
+            m = jpeg[i + 1]
+            if m in (0xC0, 0xC1, 0xC2):
+                return (jpeg[i + 5] << 8) | jpeg[i + 6], (jpeg[i + 7] << 8) | jpeg[i + 8]
+            if m == 0xFF or 0xD0 <= m <= 0xD9 or m == 0x01:
+                i += 2 if m != 0xFF else 1
+                continue
+            i += 2 + ((jpeg[i + 2] << 8) | jpeg[i + 3])
+        raise ValueError("no JPEG frame header found")
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def repeat(self, k: int):
+        """The same frames k times over, as one long video (an index, no bytes are copied): benchmark input."""
+        import copy
+        out = copy.copy(self)
+        out.offsets, out.sizes = np.tile(self.offsets, k), np.tile(self.sizes, k)
+        return out
+
+
 class FrameSource:
     """Frames [start, stop) of a video as pinned batches. `source` is a file path (cv2.VideoCapture), any indexable of
     BGR uint8 frames (e.g. a numpy array [n, H, W, 3]) or a RingClip. Iterating yields (pinned buffer [batch, H, W, 3],
@@ -195,7 +260,7 @@ class FrameSource:
 
 def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int = 32, cnn_params=None, engine=None,
                   rng_state: int = None, rank: int = None, world: int = None, gather: bool = True, pipeline=None,
-                  decoders: int = 1, depth: int = 3, stats: dict = None):
+                  decoders: int = 1, depth: int = 3, stats: dict = None, ingest: str = "host"):
     """Board states of every frame of a video under one board homography `mtx` (a fixed camera: the reference's manual
     board finder). Returns {name: array [n_frames, ...]} — "stones"/"keep"/"conf" (neural), "km_stones"/"km_trusted"
     (clustering: full-board find_stones per frame, RNG state replayed per frame index so that the result does not depend
@@ -205,28 +270,59 @@ def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int
     `pipeline`: an existing DetectPipeline to reuse (anything with its detect_stream / eng interface). `decoders`: decoder
     threads of this rank, each with `depth` pinned batch buffers (page-locking memory is slow: keep batch x depth x
     decoders modest, e.g. 16 x 3 x 8 frames of 1080p = 2.4 GB) (file sources; the streaming mode "full" needs frame order and uses one). `stats`, if given,
-    receives {"frames": frames this rank processed, "range": (start, stop)}."""
+    receives {"frames": frames this rank processed, "range": (start, stop)}.
+    ingest = "nvjpeg" (Motion-JPEG AVI files only, stateless modes): the compressed frames cross PCIe and are decoded on
+    the device by nvJPEG straight into the buffer the warp reads (csrc/jpeg_ingest.cu) — no host decode, a tenth of the
+    upload; the decoded pixels can differ from FFmpeg's by a level or two, hence not the default."""
     import collections
     import torch.distributed as dist
     from .engine import rng_seed, rng_advance
     have_group = dist.is_available() and dist.is_initialized()
     if rank is None or world is None:
         rank, world = (dist.get_rank(), dist.get_world_size()) if have_group else (0, 1)
-    n_total, H, W = probe(source)
+    avi = None
+    if ingest == "nvjpeg":
+        if not isinstance(source, (str, MjpegAvi)) or mode == "full":
+            raise ValueError('ingest="nvjpeg" needs a Motion-JPEG AVI file (path or MjpegAvi) and a stateless mode')
+        avi = source if isinstance(source, MjpegAvi) else MjpegAvi(source)
+        n_total, H, W = len(avi), avi.H, avi.W      # the index is exact (the header's frame count is an estimate)
+    else:
+        n_total, H, W = probe(source)
     if have_group and world > 1:       # every rank must shard the same count: rank 0's view of the file wins
         obj = [n_total]
         dist.broadcast_object_list(obj, src=0)
         n_total = int(obj[0])
     start, stop = sharding.shard_range(n_total, rank, world)
-    src = FrameSource(source, start, stop, batch=batch, depth=depth, decoders=1 if mode == "full" else decoders)
     pipe = pipeline or DetectPipeline(H, W, gsize, mode=mode, sub_batch=min(16, batch), cnn_params=cnn_params, engine=engine)
     st0 = rng_seed(0) if rng_state is None else rng_state
     inflight = collections.deque()
+    if avi is None:
+        src = FrameSource(source, start, stop, batch=batch, depth=depth, decoders=1 if mode == "full" else decoders)
 
-    def batches():
-        for buf, m, pos in src:
-            inflight.append((buf, m, pos))
-            yield buf[:m], mtx, rng_advance(st0, pos)
+        def batches():
+            for buf, m, pos in src:
+                inflight.append((buf, m, pos))
+                yield buf[:m], mtx, rng_advance(st0, pos)
+    else:
+        class _NoRelease:
+            @staticmethod
+            def release(buf):
+                pass
+        src = _NoRelease
+        eng = pipe.eng
+        ring = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device=eng.device) for _ in range(pipe.DEPTH + 1)]
+
+        def batches():
+            k = 0
+            for pos in range(start, stop, batch):
+                m = min(batch, stop - pos)
+                d = ring[k % len(ring)]          # free again: at most DEPTH batches are outstanding
+                k += 1
+                with torch.cuda.stream(pipe.comp_stream):
+                    eng.jpeg_decode(avi.base_address, avi.offsets[pos:pos + m], avi.sizes[pos:pos + m], d,
+                                    cpu_threads=max(1, decoders))
+                inflight.append((None, m, pos))
+                yield d[:m], mtx, rng_advance(st0, pos)
 
     names = {"neural": ("stones", "keep", "conf"), "clustering": ("km_stones", "km_trusted"),
              "both": ("stones", "keep", "conf", "km_stones", "km_trusted"),

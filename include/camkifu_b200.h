@@ -190,6 +190,18 @@ int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, int H, int W
                       size_t h_frame_pitch, const int *roi4, uint8_t *d_frames, size_t d_row_pitch,
                       size_t d_frame_pitch, void *stream);
 
+/* ---- Motion-JPEG ingest on the device (optional) ------------------------------------------------------
+ * Replaces, for MJPG files: CaptureReader.read_file -> cv2.VideoCapture.read                 vmanager.py:563-586
+ * h_jpeg / h_sizes: n compressed frames in HOST memory (consumed before the call returns); every frame must decode to
+ * H x W. d_frames: n x H x W x 3 uint8 BGR interleaved on the device (pitches in bytes), decoded by nvJPEG (a CUDA-toolkit
+ * library: the hardware JPEG engines when available, else its CUDA decoder) on `stream`. cpu_threads: host threads the
+ * library may use for its CPU stages. The pixels may differ from FFmpeg's decode of the same frame by a level or two
+ * (different IDCT / upsampling), which is why this is an option of the batch API, not the default ingest.
+ * ckb_jpeg_backend: which nvJPEG backend the context got. */
+int ckb_jpeg_decode(ckb_ctx *ctx, const uint8_t *const *h_jpeg, const size_t *h_sizes, int n, int H, int W, uint8_t *d_frames,
+                    size_t row_pitch, size_t frame_pitch, int cpu_threads, void *stream);
+const char *ckb_jpeg_backend(ckb_ctx *ctx);
+
 /* ---- per-kernel timing (bench.py's roofline) ---------------------------------------------------------------------------
  * Between ckb_profile_begin and ckb_profile_end the library records a CUDA event on the caller's stream after every
  * kernel it launches (up to `capacity` events). ckb_profile_end waits for the last one and returns, per launch in issue

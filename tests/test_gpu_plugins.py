@@ -261,3 +261,38 @@ def test_sfclustering_regions_delegate_equals_serial_calls(golden):
         if s is not None:
             assert np.array_equal(codes(s), codes(t))
     assert any(s is not None for s in serial)
+
+
+def test_nvjpeg_ingest_matches_host_decode(tmp_path):
+    """Motion-JPEG ingest on the device (process_video(ingest="nvjpeg"), csrc/jpeg_ingest.cu): the frames nvJPEG decodes
+    differ from OpenCV / FFmpeg's decode of the same file by a few levels at most, and the k-means board states of the
+    two ingests are identical."""
+    import cv2
+    from camkifu_b200.engine import StoneEngine, rng_seed
+    from camkifu_b200.video import MjpegAvi, process_video
+    n, H, W = 24, 480, 640
+    frames, mtx, truth, _ = synth.make_clip(13, n, H, W)
+    path = str(tmp_path / "clip_mjpg.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30, (W, H))
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    avi = MjpegAvi(path)
+    assert (len(avi), avi.H, avi.W) == (n, H, W)
+    eng = StoneEngine(19)
+    if eng.jpeg_backend() == "unavailable":
+        pytest.skip("libnvjpeg is not present on this machine")
+    d = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+    eng.jpeg_decode(avi.base_address, avi.offsets, avi.sizes, d)
+    cap = cv2.VideoCapture(path)
+    host = np.stack([cap.read()[1] for _ in range(n)])
+    cap.release()
+    diff = np.abs(d.cpu().numpy().astype(np.int16) - host.astype(np.int16))
+    assert diff.max() <= 6 and diff.mean() < 0.5
+    st0 = rng_seed(2)
+    a = process_video(path, mtx, mode="clustering", batch=8, engine=eng, rng_state=st0)
+    b = process_video(path, mtx, mode="clustering", batch=8, engine=eng, rng_state=st0, ingest="nvjpeg")
+    assert np.array_equal(a["km_stones"], b["km_stones"]) and np.array_equal(a["km_stones"], truth)
+    assert np.array_equal(a["km_trusted"], b["km_trusted"])
+    c = process_video(avi.repeat(2), mtx, mode="clustering", batch=16, engine=eng, rng_state=st0, ingest="nvjpeg")
+    assert c["km_stones"].shape[0] == 2 * n and np.array_equal(c["km_stones"][:n], b["km_stones"])

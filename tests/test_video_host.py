@@ -86,3 +86,41 @@ def test_ring_clip_is_zero_copy():
         pos += m
         src.release(buf)
     assert pos == 23
+
+
+def test_mjpeg_avi_index(tmp_path):
+    """MjpegAvi (the index the device-side JPEG ingest reads): one entry per frame in file order, each a complete JPEG
+    (SOI ... EOI) of the size the container declares; repeat() tiles the index; other containers are refused."""
+    import cv2
+    from camkifu_b200.video import MjpegAvi
+    n, H, W = 7, 48, 64
+    rng = np.random.default_rng(0)
+    path = str(tmp_path / "m.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 30, (W, H))
+    ramp = np.add.outer(np.arange(H), np.arange(W))[:, :, None] % 64
+    frames = [(ramp + rng.integers(0, 192, 3)[None, None, :]).astype(np.uint8) for _ in range(n)]   # smooth, distinct
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    avi = MjpegAvi(path)
+    assert (len(avi), avi.H, avi.W) == (n, H, W)
+    assert np.all(np.diff(avi.offsets) > 0) and np.all(avi.sizes > 0)
+    raw = np.fromfile(path, dtype=np.uint8)
+    for i in range(n):
+        blob = raw[avi.offsets[i]: avi.offsets[i] + avi.sizes[i]]
+        assert blob[0] == 0xFF and blob[1] == 0xD8
+        img = cv2.imdecode(blob, cv2.IMREAD_COLOR)
+        assert img.shape == (H, W, 3)
+    cap = cv2.VideoCapture(path)
+    ok, first = cap.read()
+    cap.release()
+    # the indexed chunk is the frame the container's decoder returns (two JPEG decoders: chroma upsampling differs)
+    mine = cv2.imdecode(raw[avi.offsets[0]: avi.offsets[0] + avi.sizes[0]], cv2.IMREAD_COLOR)
+    assert ok and np.abs(first.astype(np.int16) - mine.astype(np.int16)).mean() < 3
+    assert np.abs(first.astype(np.int16) - frames[1].astype(np.int16)).mean() > 10
+    rep = avi.repeat(3)
+    assert len(rep) == 3 * n and np.array_equal(rep.offsets[n:2 * n], avi.offsets) and (rep.H, rep.W) == (H, W)
+    other = tmp_path / "not_avi.bin"
+    other.write_bytes(b"\x00" * 64)
+    with pytest.raises(ValueError):
+        MjpegAvi(str(other))
