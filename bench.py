@@ -589,23 +589,37 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     from camkifu_b200.video import MjpegAvi
     vj = None
     if not args.quick:
+        # every rank first checks, on its own, that nvJPEG is there and decodes (no collective yet): the leg runs only if
+        # all of them can, so that a rank without the library cannot leave the others waiting in the final gather
         try:
-            long_avi = MjpegAvi(vfile).repeat(max(1, 512 * world // vfile_frames))
+            short_avi = MjpegAvi(vfile)
+            probe = torch.empty((2, short_avi.H, short_avi.W, 3), dtype=torch.uint8, device=dev)
+            eng.jpeg_decode(short_avi.base_address, short_avi.offsets[:2], short_avi.sizes[:2], probe)
+            torch.cuda.synchronize()
+            vj_why = None if eng.jpeg_backend() != "unavailable" else "libnvjpeg not found"
+            del probe
+        except Exception as e:       # noqa: BLE001 - an optional leg: report why it is missing
+            vj_why = repr(e)
+        flag = torch.tensor([0.0 if vj_why else 1.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) > 0:
+            long_avi = short_avi.repeat(max(1, 512 * world // vfile_frames))
 
             def timed_nvjpeg():
+                barrier()
                 v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 v0.record()
                 o = process_video(long_avi, mtx, mode="neural", batch=256, pipeline=vpipe, decoders=2, ingest="nvjpeg")
                 v1.record()
-                barrier()
+                torch.cuda.synchronize()
                 return v0.elapsed_time(v1) / 1e3, o["stones"].shape[0]
             timed_nvjpeg()                      # page-locks / allocates the decoder's buffers
             vj_s, vj_n = timed_nvjpeg()
             vj = {"seconds": vj_s, "frames": vj_n, "backend": eng.jpeg_backend(),
                   "mb_per_frame": float(long_avi.sizes.mean()) / 1e6}
-        except Exception as e:       # noqa: BLE001 - an optional leg: report why it is missing
-            vj = {"error": repr(e)}
-            barrier()
+        else:
+            vj = {"unavailable": vj_why or "nvJPEG unavailable on another rank"}
 
     # ---- per-rank step times and clocks of the headline leg (the max over ranks is what is reported; this shows whether a
     # gap to N x the single-GPU value is one slow GPU or all of them)

@@ -171,79 +171,114 @@ int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softm
 }
 
 // Tail of the tensor-core path (cnn_tc.cu): fc2 (Dense(81), nn_manager.py:295; 13 k MAC per patch, float32 FMA in the
-// same sequential order as cnn_dense_simt) + softmax + label / confidence in one kernel. One warp per region: the 160
-// inputs sit in registers (5 per lane) and are broadcast by shuffles, each lane owns outputs lane, lane + 32, lane + 64,
-// the 160 x 81 weights are staged once per block in shared memory.
+// same sequential order as cnn_dense_simt) + softmax + label / confidence in one kernel. The 160 x 81 weights are
+// staged once per block in shared memory; a warp takes FC2_R regions at a time so that every weight it reads from shared
+// memory feeds FC2_R FMAs (one region per warp made the kernel LSU-bound: 3 LDS + 1 SHFL per 3 FMA). The regions' 160
+// inputs sit in shared memory too and are read as broadcast 16-byte loads; each lane owns outputs lane, lane + 32,
+// lane + 64 of every region. The label / confidence walk (sequential float32 sum, first maximum) runs on FC2_R lanes at
+// once, one region each.
 #define FC2_THREADS 256
-#define FC2_SMEM ((CNN_F5 * CNN_F6 + CNN_F6) * 4)
+#define FC2_R 4
+#define FC2_WFLOATS ((CNN_F5 * CNN_F6 + CNN_F6 + 3) / 4 * 4)
+#define FC2_SMEM ((FC2_WFLOATS + (FC2_THREADS / 32) * FC2_R * CNN_F5) * 4)
+static_assert((OFF_W6 % 4) == 0 && (CNN_F5 * CNN_F6) % 4 == 0 && CNN_F5 % 4 == 0, "16-byte loads of fc2's weights / inputs");
 __global__ void __launch_bounds__(FC2_THREADS) cnn_fc2_softmax_label(const float *__restrict__ f5, const float *__restrict__ w,
                                                                      const float *__restrict__ b, int n_regions,
                                                                      float *__restrict__ softmax, int *__restrict__ label,
                                                                      float *__restrict__ conf)
 {
-    extern __shared__ float s_w[];                       // [160][81] weights, then [81] biases
-    for (int i = threadIdx.x; i < CNN_F5 * CNN_F6; i += FC2_THREADS) s_w[i] = __ldg(w + i);
-    for (int i = threadIdx.x; i < CNN_F6; i += FC2_THREADS) s_w[CNN_F5 * CNN_F6 + i] = __ldg(b + i);
+    extern __shared__ __align__(16) float s_w[];         // [160][81] weights, [81] biases, then [warp][FC2_R][160] inputs
+    {
+        const float4 *w4 = (const float4 *)w;
+        float4 *s4 = (float4 *)s_w;
+#pragma unroll 13
+        for (int i = threadIdx.x; i < CNN_F5 * CNN_F6 / 4; i += FC2_THREADS) s4[i] = __ldg(w4 + i);
+        for (int i = threadIdx.x; i < CNN_F6; i += FC2_THREADS) s_w[CNN_F5 * CNN_F6 + i] = __ldg(b + i);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool has2 = lane + 64 < CNN_F6;
-    for (int reg = blockIdx.x * (FC2_THREADS / 32) + wib; reg < n_regions; reg += gridDim.x * (FC2_THREADS / 32)) {
-        const float *x = f5 + (size_t)reg * CNN_F5;
-        float xin[5];
+    float *s_x = s_w + FC2_WFLOATS + wib * (FC2_R * CNN_F5);
+    const int n_groups = (n_regions + FC2_R - 1) / FC2_R;
+    for (int grp = blockIdx.x * (FC2_THREADS / 32) + wib; grp < n_groups; grp += gridDim.x * (FC2_THREADS / 32)) {
+        const int reg0 = grp * FC2_R;
+        const int nr = min(FC2_R, n_regions - reg0);
+        __syncwarp();                                    // the previous group's walk has finished with s_x
+        {   // the group's inputs: FC2_R x 160 consecutive floats of f5
+            const float4 *x4 = (const float4 *)(f5 + (size_t)reg0 * CNN_F5);
+            float4 *d4 = (float4 *)s_x;
 #pragma unroll
-        for (int k = 0; k < 5; k++) xin[k] = __ldg(x + 32 * k + lane);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-#pragma unroll 8
-            for (int l = 0; l < 32; l++) {
-                const float xi = __shfl_sync(0xffffffffu, xin[k], l);
-                const float *wr = s_w + (32 * k + l) * CNN_F6;
-                a0 = fmaf(xi, wr[lane], a0);
-                a1 = fmaf(xi, wr[lane + 32], a1);
-                if (has2) a2 = fmaf(xi, wr[lane + 64], a2);
-            }
+            for (int i = lane; i < FC2_R * CNN_F5 / 4; i += 32)
+                d4[i] = i < nr * (CNN_F5 / 4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float v[3];
-        v[0] = a0 + s_w[CNN_F5 * CNN_F6 + lane];
-        v[1] = a1 + s_w[CNN_F5 * CNN_F6 + lane + 32];
-        v[2] = has2 ? a2 + s_w[CNN_F5 * CNN_F6 + lane + 64] : -INFINITY;
-        float m = fmaxf(fmaxf(v[0], v[1]), v[2]);
+        __syncwarp();
+        float a0[FC2_R], a1[FC2_R], a2[FC2_R];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float s = 0.f;
+        for (int r = 0; r < FC2_R; r++) a0[r] = a1[r] = a2[r] = 0.f;
+#pragma unroll 2
+        for (int k4 = 0; k4 < CNN_F5 / 4; k4++) {
+            float4 xv[FC2_R];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            v[k] = (lane + 32 * k) < CNN_F6 ? expf(v[k] - m) : 0.f;
-            s += v[k];
-        }
+            for (int r = 0; r < FC2_R; r++) xv[r] = *(const float4 *)(s_x + r * CNN_F5 + 4 * k4);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        float *y = softmax + (size_t)reg * CNN_F6;
+            for (int kk = 0; kk < 4; kk++) {
+                const float *wr = s_w + (4 * k4 + kk) * CNN_F6;
+                // lanes without a third output read into the next weight row (inside the array): the value is unused
+                const float w0 = wr[lane], w1 = wr[lane + 32], w2 = wr[lane + 64];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            v[k] = __fdiv_rn(v[k], s);
-            if (lane + 32 * k < CNN_F6) y[lane + 32 * k] = v[k];
-        }
-        // label = first maximum (np.argmax); confidence = max(y) / sum(y) with Python's sequential float32 sum
-        // (nn_cache.py:28-30): lane 0 walks the 81 values in order, fetching them from their owners by shuffle
-        int best = 0;
-        float bv = 0.f, tot = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-#pragma unroll 9
-            for (int l = 0; l < 32; l++) {
-                const float t = __shfl_sync(0xffffffffu, v[k], l);
-                const int o = 32 * k + l;
-                if (o < CNN_F6) {
-                    if (o == 0 || t > bv) { bv = t; best = o; }
-                    tot = __fadd_rn(tot, t);
+                for (int r = 0; r < FC2_R; r++) {
+                    const float xi = kk == 0 ? xv[r].x : kk == 1 ? xv[r].y : kk == 2 ? xv[r].z : xv[r].w;
+                    a0[r] = fmaf(xi, w0, a0[r]);
+                    a1[r] = fmaf(xi, w1, a1[r]);
+                    a2[r] = fmaf(xi, w2, a2[r]);
                 }
             }
         }
-        if (lane == 0) {
-            label[reg] = best;
-            conf[reg] = __fdiv_rn(bv, tot);
+        __syncwarp();                                    // all lanes are done with the inputs: s_x now takes the softmax
+        const float bias0 = s_w[CNN_F5 * CNN_F6 + lane], bias1 = s_w[CNN_F5 * CNN_F6 + lane + 32];
+        const float bias2 = has2 ? s_w[CNN_F5 * CNN_F6 + lane + 64] : 0.f;
+#pragma unroll
+        for (int r = 0; r < FC2_R; r++) {
+            float v[3];
+            v[0] = a0[r] + bias0;
+            v[1] = a1[r] + bias1;
+            v[2] = has2 ? a2[r] + bias2 : -INFINITY;
+            float m = fmaxf(fmaxf(v[0], v[1]), v[2]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                v[k] = (lane + 32 * k) < CNN_F6 ? expf(v[k] - m) : 0.f;
+                s += v[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            float *y = softmax + (size_t)(reg0 + r) * CNN_F6;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                v[k] = __fdiv_rn(v[k], s);
+                if (lane + 32 * k < CNN_F6) {
+                    s_x[r * CNN_F5 + lane + 32 * k] = v[k];
+                    if (r < nr) y[lane + 32 * k] = v[k];
+                }
+            }
+        }
+        __syncwarp();
+        // label = first maximum (np.argmax); confidence = max(y) / sum(y) with Python's sequential float32 sum
+        // (nn_cache.py:28-30): lane r walks the 81 values of region r in order
+        if (lane < nr) {
+            const float *y = s_x + lane * CNN_F5;
+            int best = 0;
+            float bv = y[0], tot = 0.f;
+#pragma unroll 9
+            for (int o = 0; o < CNN_F6; o++) {
+                const float t = y[o];
+                if (t > bv) { bv = t; best = o; }
+                tot = __fadd_rn(tot, t);
+            }
+            label[reg0 + lane] = best;
+            conf[reg0 + lane] = __fdiv_rn(bv, tot);
         }
     }
 }
@@ -263,9 +298,9 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
     float *sm = d_softmax ? d_softmax : (float *)d_tmp;
     int *lab = (int *)((float *)d_tmp + (size_t)P * CNN_F6);
     float *cf = (float *)(lab + P);
-    const int per_block = FC2_THREADS / 32;
+    const int per_block = FC2_THREADS / 32 * FC2_R;
     int grid = (P + per_block - 1) / per_block;
-    if (grid > 2 * ctx->num_sms) grid = 2 * ctx->num_sms;
+    if (grid > 3 * ctx->num_sms) grid = 3 * ctx->num_sms;
     cnn_fc2_softmax_label<<<grid, FC2_THREADS, FC2_SMEM, st>>>(d_f5, w + OFF_W6, w + OFF_B6, P, sm, lab, cf);
     CKB_LAUNCH_CHECK(ctx, "cnn_fc2_softmax_label");
     cnn_decode_board<<<(n * 361 + 127) / 128, 128, 0, st>>>(lab, cf, n, d_stones, d_conf, d_keep);

@@ -41,31 +41,38 @@ int ckb_launch_fc2_decode(ckb_ctx *ctx, const float *d_f5, int n, void *d_tmp, f
 // ------------------------------------------------------------------------------------------------------ layer configs
 struct Conv1Cfg {   // geometry only (weights size), as Conv2Cfg: input = 16-channel "row window" expansion (k = dx*3 + c), taps = dy
     static constexpr int NTAPS = 5, GW = 40, HW_IN = 1600, OH = 36, OW = 36, KC = 2, N = 32, A_PLANES = 1;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false, POOL_XY = false;
     static constexpr int KCS = 2, NSTAGE = 1, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return t * 40; }
 };
 struct Conv2Cfg {   // geometry only (weights size): conv1 and conv2 run in cnn_tc_front.cu, not through cnn_tc_layer
     static constexpr int NTAPS = 25, GW = 36, HW_IN = 1296, OH = 32, OW = 32, KC = 4, N = 32, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false, POOL_XY = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 5) * 36 + t % 5; }
 };
 struct Conv3Cfg {
     static constexpr int NTAPS = 9, GW = 16, HW_IN = 256, OH = 14, OW = 14, KC = 4, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = true, OUT_F32 = false, POOL_X = false, POOL_XY = false;
     static constexpr int KCS = 4, NSTAGE = 1, NABUF = 3, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 16 + t % 3; }
 };
-struct Conv4Cfg {   // POOL_X: the epilogue already takes the horizontal half of the 2x2 max-pool that follows
+struct Conv4Cfg {   // POOL_X: the epilogue takes the horizontal half of the 2x2 max-pool that follows (lanes m, m + 1)
     static constexpr int NTAPS = 9, GW = 14, HW_IN = 196, OH = 12, OW = 12, KC = 12, N = 96, A_PLANES = 2;
-    static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false, POOL_X = true;
+    static constexpr bool CONCAT = true, A_RES = true, W_RES = false, OUT_F32 = false, POOL_X = true, POOL_XY = false;
     static constexpr int KCS = 4, NSTAGE = 8, NABUF = 2, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int t) { return (t / 3) * 14 + t % 3; }
 };
+// POOL_XY: the whole 2x2 max-pool in conv4's epilogue, written straight into fc1's per-tap planes (no a4 round trip through
+// HBM, no pooling kernel). The vertical partner of a pixel is 14 rows up: 14 lanes away in the same warp, or in the
+// previous lane quarter / the previous tile, which is why the epilogue warps exchange their last rows through shared
+// memory and every CTA takes a CONTIGUOUS range of tiles (plus the tile before it, recomputed only for its last rows).
+struct Conv4PoolCfg : Conv4Cfg {
+    static constexpr bool POOL_XY = true;
+};
 struct Fc1Cfg {     // "pixels" are patches; tap q = pooled pixel, its A tile is streamed with its weights
     static constexpr int NTAPS = 36, GW = 1, HW_IN = 1, OH = 1, OW = 1, KC = 12, N = 160, A_PLANES = 2;
-    static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true, POOL_X = false;
+    static constexpr bool CONCAT = false, A_RES = false, W_RES = false, OUT_F32 = true, POOL_X = false, POOL_XY = false;
     static constexpr int KCS = 4, NSTAGE = 5, NABUF = 0, NACC = 2;
     __host__ __device__ static constexpr int tapoff(int) { return 0; }
 };
@@ -88,7 +95,10 @@ struct Derived {
     static constexpr int ACC_COLS = L::CONCAT ? 2 * L::N : L::N;
     static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
                                      : NACC * ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int SMEM = NABUF * A_TILE + W_ALL + NSTAGE * STAGE + 320 /*barriers*/ + 128 /*align*/;
+    static constexpr int XCH_PITCH = 96;                                         // floats per exchanged row
+    static constexpr int XCH = L::POOL_XY ? 4 * 7 * XCH_PITCH * 4 : 0;           // 7 rows of each lane quarter (what is left of smem)
+    static constexpr int XCH_OFF = NABUF * A_TILE + W_ALL + NSTAGE * STAGE + 320;
+    static constexpr int SMEM = XCH_OFF + XCH + 128 /*align*/;
     static_assert(L::KC % L::KCS == 0 && L::KCS % 2 == 0, "stages hold whole K=16 steps");
     static_assert(NACC * ACC_COLS <= 512 && NACC <= 4 && NABUF <= 6, "accumulators must fit in TMEM; barrier map");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -132,7 +142,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
     static_assert(D::NSTAGE <= 8, "barrier map");
 
     const int warp = warp_index(), lane = threadIdx.x & 31;
-    const int n_my = ((int)args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tiles of this CTA: t_first + i * t_step, i < n_my. Strided over the grid, or (POOL_XY) a contiguous range preceded
+    // by the tile before it ("lead": computed for the rows the first real tile pools with, nothing of it is stored)
+    int t_first = (int)blockIdx.x, t_step = (int)gridDim.x;
+    int n_my = ((int)args.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    bool lead = false;
+    if constexpr (L::POOL_XY) {
+        const int base = args.n_tiles / (int)gridDim.x, extra = args.n_tiles % (int)gridDim.x;
+        const int start = (int)blockIdx.x * base + min((int)blockIdx.x, extra);
+        lead = start > 0;
+        t_first = start - (lead ? 1 : 0);
+        t_step = 1;
+        n_my = base + ((int)blockIdx.x < extra ? 1 : 0) + (lead ? 1 : 0);
+    }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 6; i++) {
@@ -173,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
             }
             uint32_t sit = 0;  // stage counter
             for (int i = 0; i < n_my; i++) {
-                const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const long long tile = (long long)t_first + (long long)i * t_step;
                 if constexpr (L::A_RES) {
                     const int ab = i % D::NABUF;
                     mbar_wait(b_aempty + 8 * ab, ((i / D::NABUF) & 1) ^ 1);
@@ -272,8 +294,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_layer(const __grid_const
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                // which column chunks (j = half, half + 2, ...) it handles
         const int row = q * 32 + lane;
+        if constexpr (L::POOL_XY) {
+            // conv4 + ReLU + 2x2 max-pool -> fc1's tap planes. Grid rows are GW = 14 pixels: the pixel above row r of a
+            // tile is row r - 14. Odd-y pixels ("lower") fetch their upper neighbour's values (already maxed with x + 1) by
+            // a shuffle from lane - 14, or for lanes < 14 from the rows the previous quarter's warp (for quarter 0: quarter 3
+            // of the previous tile) left in shared memory, and store the pooled pixel.
+            static_assert(L::GW == 14 && L::OH == 12 && L::OW == 12 && L::N == 96 && TC_EPI_WARPS == 8, "conv4 geometry");
+            constexpr int NJ = 6, XP = D::XCH_PITCH;
+            float *xch = (float *)(smem + D::XCH_OFF);
+            const uint32_t bar_id = 1 + half;            // the four warps (quarters) that share this half's column chunks
+            for (int i = 0; i < n_my; i++) {
+                const int tile = t_first + i;
+                const int acc = i % D::NACC;
+                const int p = tile * 128 + row;
+                const int patch = p / L::HW_IN;
+                const int rem = p - patch * L::HW_IN;
+                const int y = rem / L::GW, x = rem - y * L::GW;
+                const bool lower = patch < args.n_patches && (y & 1) && y < L::OH && x < L::OW && !(x & 1) && !(lead && i == 0);
+                const int qtap = (y >> 1) * (L::OW / 2) + (x >> 1);
+                mbar_wait(b_tfull + 8 * acc, (i / D::NACC) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * D::ACC_COLS;
+                float vv[NJ][8], uu[NJ][8];
+#pragma unroll
+                for (int jj = 0; jj < NJ; jj++) {
+                    const int j = half + jj * 2;
+                    tc_ld8(taddr + 8 * j, vv[jj]);
+                    tc_ld8(taddr + L::N + 8 * j, uu[jj]);
+                }
+                tc_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+#pragma unroll
+                for (int jj = 0; jj < NJ; jj++) {
+                    const int j = half + jj * 2;
+                    float *v = vv[jj];
+                    const float4 b0 = __ldg((const float4 *)args.bias + 2 * j), b1 = __ldg((const float4 *)args.bias + 2 * j + 1);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        v[k] = fmaxf(v[k] + uu[jj][k] + bb[k], 0.f);
+                        v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], 1));
+                    }
+                }
+                // the last 14 rows of the quarter (their even-x lanes: 18, 20, ... 30) for the next quarter's lanes < 14.
+                // Quarter 3's rows are for quarter 0 of the NEXT tile, which still reads the previous ones in this
+                // iteration: they are published after the second barrier instead.
+                float *dst = xch + (q * 7 + ((lane - 18) >> 1)) * XP;
+                const bool pub = lane >= 18 && !(lane & 1);
+                if (pub && q < 3) {
+#pragma unroll
+                    for (int jj = 0; jj < NJ; jj++) {
+                        const int j = half + jj * 2;
+                        *(float4 *)(dst + 8 * j) = make_float4(vv[jj][0], vv[jj][1], vv[jj][2], vv[jj][3]);
+                        *(float4 *)(dst + 8 * j + 4) = make_float4(vv[jj][4], vv[jj][5], vv[jj][6], vv[jj][7]);
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                const float *src = xch + (((q + 3) & 3) * 7 + (lane >> 1)) * XP;
+#pragma unroll
+                for (int jj = 0; jj < NJ; jj++) {
+                    const int j = half + jj * 2;
+                    float u[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) u[k] = __shfl_up_sync(0xffffffffu, vv[jj][k], 14);
+                    if (lower) {
+                        if (lane < 14) {
+                            const float4 s0 = *(const float4 *)(src + 8 * j), s1 = *(const float4 *)(src + 8 * j + 4);
+                            u[0] = s0.x; u[1] = s0.y; u[2] = s0.z; u[3] = s0.w;
+                            u[4] = s1.x; u[5] = s1.y; u[6] = s1.z; u[7] = s1.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) u[k] = fmaxf(u[k], vv[jj][k]);
+                        uint4 hi, lo;
+                        split8(u, hi, lo);
+                        args.out[(long long)(qtap * L::KC + j) * args.out_plane + patch] = hi;
+                        args.out[(long long)((L::OH / 2 * (L::OW / 2) + qtap) * L::KC + j) * args.out_plane + patch] = lo;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the exchange rows may be overwritten
+                if (pub && q == 3) {
+#pragma unroll
+                    for (int jj = 0; jj < NJ; jj++) {
+                        const int j = half + jj * 2;
+                        *(float4 *)(dst + 8 * j) = make_float4(vv[jj][0], vv[jj][1], vv[jj][2], vv[jj][3]);
+                        *(float4 *)(dst + 8 * j + 4) = make_float4(vv[jj][4], vv[jj][5], vv[jj][6], vv[jj][7]);
+                    }
+                }
+            }
+        } else
         for (int i = 0; i < n_my; i++) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tile = t_first + i * t_step;
             const int acc = i % D::NACC;
             const int p = tile * 128 + row;              // flat pixel of the input grid (< 2^31 for 64 frames)
             const int patch = p / L::HW_IN;
@@ -351,45 +463,6 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float *v
     for (int i = 0; i < 4; i++) {
         v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
         v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
-    }
-}
-
-// Vertical half of the 2x2 max pooling after conv4 (its epilogue already took the horizontal half): hi/lo planes
-// [2][KC][in_plane] on an H x WP grid per patch -> fc1's per-tap planes, tap q = oy * WP + ox:
-//   out[((q * KC + chunk) * out_plane + patch]  (hi),  out[((H/2 * WP + q) * KC + chunk) * out_plane + patch]  (lo)
-// The input is patch-major, the output patch-minor: one block stages the (contiguous) units of PB patches of one chunk in
-// shared memory with coalesced 16-byte loads, then writes every tap as a run of PB consecutive patches.
-#define POOL_PB 16
-template <int H, int WP, int KC>
-__global__ void __launch_bounds__(256) cnn_tc_pool_rows(const uint4 *__restrict__ in, long long in_plane, int n_patches,
-                                                        uint4 *__restrict__ out, long long out_plane)
-{
-    constexpr int OH = H / 2, UNITS = H * WP, PITCH = UNITS + 1;   // +1: patches fall in different banks
-    __shared__ uint4 s_hi[POOL_PB * PITCH], s_lo[POOL_PB * PITCH];
-    const int c = blockIdx.y, p0 = blockIdx.x * POOL_PB;
-    const int np = min(POOL_PB, n_patches - p0);
-    const uint4 *gh = in + (long long)c * in_plane + (long long)p0 * UNITS;
-    const uint4 *gl = in + (long long)(KC + c) * in_plane + (long long)p0 * UNITS;
-    for (int u = threadIdx.x; u < np * UNITS; u += blockDim.x) {
-        const int p = u / UNITS, r = u - p * UNITS;
-        s_hi[p * PITCH + r] = __ldg(gh + u);
-        s_lo[p * PITCH + r] = __ldg(gl + u);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < OH * WP * POOL_PB; t += blockDim.x) {
-        const int p = t % POOL_PB, q = t / POOL_PB;
-        if (p >= np) continue;
-        const int oy = q / WP, ox = q - oy * WP;
-        const int r = (2 * oy) * WP + ox;
-        float m[8], v[8];
-        unpack8(s_hi[p * PITCH + r], s_lo[p * PITCH + r], m);
-        unpack8(s_hi[p * PITCH + r + WP], s_lo[p * PITCH + r + WP], v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], v[k]);
-        uint4 hi, lo;
-        split8(m, hi, lo);
-        out[((long long)q * KC + c) * out_plane + p0 + p] = hi;
-        out[((long long)(OH * WP + q) * KC + c) * out_plane + p0 + p] = lo;
     }
 }
 
@@ -510,7 +583,7 @@ int ckb_cnn_tc_pack(ckb_ctx *ctx, const float *p)
     ctx->cnn->tc_bytes = L.total;
     // opt in to the large dynamic shared memory footprints once
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv3Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv3Cfg>::SMEM));
-    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4Cfg>::SMEM));
+    CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Conv4PoolCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Conv4PoolCfg>::SMEM));
     CKB_CUDA(ctx, cudaFuncSetAttribute(cnn_tc_layer<Fc1Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<Fc1Cfg>::SMEM));
     const int rc = ckb_cnn_tail_init(ctx);
     if (rc != CKB_OK) return rc;
@@ -527,8 +600,8 @@ void ckb_cnn_tc_free(ckb_ctx *ctx)
 
 struct TcWork {
     // plane strides in 16-byte units (pixels), each with a tail so that the last tile's halo read stays inside
-    long long a1_plane, p2_plane, a3_plane, a4_plane, p4_plane;
-    size_t a1, p2, a3, a4, p4, f5, tmp, total;
+    long long a1_plane, p2_plane, a3_plane, p4_plane;
+    size_t a1, p2, a3, p4, f5, tmp, total;
 };
 
 static long long plane_units(long long pixels, int halo) { return ((pixels + 127) / 128 * 128 + halo + 7) / 8 * 8; }
@@ -541,13 +614,11 @@ static TcWork tc_work_layout(int nf, bool dump_a1)
     w.a1_plane = dump_a1 ? plane_units(P * 1296, 0) : 0;
     w.p2_plane = plane_units(P * 256, Derived<Conv3Cfg>::HALO);
     w.a3_plane = plane_units(P * 196, Derived<Conv4Cfg>::HALO);
-    w.a4_plane = plane_units(P * 72, 0);          // conv4 output after the horizontal half of the pooling: 12 x 6
     w.p4_plane = plane_units(P, 0);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
     w.p2 = take((size_t)w.p2_plane * 16 * 8);
     w.a3 = take((size_t)w.a3_plane * 16 * 24);
-    w.a4 = take((size_t)w.a4_plane * 16 * 24);
     w.p4 = take((size_t)w.p4_plane * 16 * 2 * 36 * 12);
     w.f5 = take((size_t)P * 160 * 4);
     w.tmp = take((size_t)P * (81 + 81 + 2) * 4);
@@ -595,7 +666,7 @@ static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t
     const TcWork W = tc_work_layout(nf, dump);
     const TcBlob B = blob_layout();
     const int P = nf * 100;
-    uint4 *p2 = (uint4 *)(work + W.p2), *a3 = (uint4 *)(work + W.a3), *a4 = (uint4 *)(work + W.a4);
+    uint4 *p2 = (uint4 *)(work + W.p2), *a3 = (uint4 *)(work + W.a3);
     uint4 *p4 = (uint4 *)(work + W.p4);
     float *f5 = (float *)(work + W.f5);
     const uint8_t *tc = (const uint8_t *)ctx->cnn->d_tc;
@@ -604,10 +675,9 @@ static int tc_forward_pass(ckb_ctx *ctx, const uint8_t *d_goban, int nf, uint8_t
                                 (const float *)(tc + B.off_b[1]), p2, W.p2_plane, dump ? work + W.a1 : nullptr, W.a1_plane, st));
     TC_TRY(launch_layer<Conv3Cfg>(ctx, "cnn_tc_conv3", p2, W.p2_plane, B.off_w[2], B.off_b[2], a3, W.a3_plane, nullptr,
                                   (long long)P * 256, P, st));
-    TC_TRY(launch_layer<Conv4Cfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], a4, W.a4_plane, nullptr,
-                                  (long long)P * 196, P, st));
-    cnn_tc_pool_rows<12, 6, 12><<<dim3((unsigned)((P + POOL_PB - 1) / POOL_PB), 12), 256, 0, st>>>(a4, W.a4_plane, P, p4, W.p4_plane);
-    CKB_LAUNCH_CHECK(ctx, "cnn_tc_pool4");
+    // conv4 + ReLU + the second 2x2 max-pool, written as fc1's per-tap planes
+    TC_TRY(launch_layer<Conv4PoolCfg>(ctx, "cnn_tc_conv4", a3, W.a3_plane, B.off_w[3], B.off_b[3], p4, W.p4_plane, nullptr,
+                                      (long long)P * 196, P, st));
     TC_TRY(launch_layer<Fc1Cfg>(ctx, "cnn_tc_fc1", p4, W.p4_plane, B.off_w[4], B.off_b[4], nullptr, 0, f5, P, P, st));
     return ckb_launch_fc2_decode(ctx, f5, nf, work + W.tmp, d_softmax, d_stones, d_conf, d_keep, st);
 }
