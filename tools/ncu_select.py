@@ -14,7 +14,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__block_size", "launch__cluster_dim_x", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__shared_mem_per_block_dynamic",
         "launch__shared_mem_per_block_static", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "sm__cycles_active.avg", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
+        "sm__cycles_active.avg", "sm__cycles_elapsed.avg.per_second", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
         "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
