@@ -584,8 +584,8 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
     barrier()
     vfile_s, vfile_n, vfile_mine = timed_video(vfile, decoders, 16)
     # (iii) the same file decoded on the device: the compressed frames cross PCIe, nvJPEG decodes 256-frame batches into
-    # the buffer the warp reads (csrc/jpeg_ingest.cu). The file's frames repeated to 512 per rank: nvJPEG's GPU Huffman
-    # path needs batches of more than 100 frames.
+    # the buffer the warp reads (csrc/jpeg_ingest.cu), three decoder lanes side by side. The file's frames repeated to 2048
+    # per rank: nvJPEG's GPU Huffman path needs batches of more than 100 frames.
     from camkifu_b200.video import MjpegAvi
     vj = None
     if not args.quick:
@@ -604,13 +604,13 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if float(flag) > 0:
-            long_avi = short_avi.repeat(max(1, 512 * world // vfile_frames))
+            long_avi = short_avi.repeat(max(1, 2048 * world // vfile_frames))      # 8 batches of 256 per rank
 
             def timed_nvjpeg():
                 barrier()
                 v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 v0.record()
-                o = process_video(long_avi, mtx, mode="neural", batch=256, pipeline=vpipe, decoders=2, ingest="nvjpeg")
+                o = process_video(long_avi, mtx, mode="neural", batch=256, pipeline=vpipe, decoders=3, ingest="nvjpeg")
                 v1.record()
                 torch.cuda.synchronize()
                 return v0.elapsed_time(v1) / 1e3, o["stones"].shape[0]
@@ -760,7 +760,7 @@ def run_b200(args, rank, world, local_rank, gpu_index, gpu_map):
                       "file_nvjpeg": ({"value": vj["frames"] / vj["seconds"], "unit": UNIT, "frames": vj["frames"],
                                        "seconds": vj["seconds"], "backend": vj["backend"],
                                        "source": "the same MJPG frames (%.2f MB each) looped to %d frames, decoded on the device "
-                                                 "in 256-frame batches (process_video(ingest='nvjpeg')): compressed frames cross "
+                                                 "in 256-frame batches by 3 nvJPEG lanes per rank (process_video(ingest='nvjpeg', decoders=3)): compressed frames cross "
                                                  "PCIe; pixels differ from the host decoder's by <= 3 levels, k-means board states "
                                                  "identical (tools/nvjpeg_probe.py, tests)" % (vj["mb_per_frame"], vj["frames"]),
                                        "limiter": "nvJPEG decode on the GPU"} if vj and "seconds" in vj else vj)},

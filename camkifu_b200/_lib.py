@@ -52,7 +52,7 @@ SIGNATURES = {
     "ckb_upload_frames": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _i32p, _u8p,
                                     C.c_size_t, C.c_size_t, C.c_void_p]),
     "ckb_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p, C.c_size_t, C.c_size_t,
-                                  C.c_int, C.c_void_p]),
+                                  C.c_int, C.c_int, C.c_void_p]),
     "ckb_jpeg_backend": (C.c_char_p, [C.c_void_p]),
     "ckb_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "ckb_profile_end": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _f32p, _i32p]),

@@ -10,6 +10,7 @@
 
 #define CKB_MAX_G 19
 #define CKB_MAX_ZONES (CKB_MAX_G * CKB_MAX_G)
+#define CKB_JPEG_LANES 8   // independent nvJPEG decoders per context (ckb_jpeg_decode's `lane`)
 
 struct ckb_cnn_weights;  // cnn_pack.cu
 struct ckb_jpeg_state;   // jpeg_ingest.cu
@@ -31,7 +32,7 @@ struct ckb_ctx {
     uint8_t *d_mask;    // [S*S] disk mask
     int32_t h_rects[CKB_MAX_ZONES * 4];
     ckb_cnn_weights *cnn;
-    struct ckb_jpeg_state *jpeg;   // nvJPEG handles of the Motion-JPEG ingest (jpeg_ingest.cu), created on first use
+    struct ckb_jpeg_state *jpeg[CKB_JPEG_LANES];   // nvJPEG decoders of the Motion-JPEG ingest (jpeg_ingest.cu), created on first use
     // per-kernel timing (ckb_profile_begin / ckb_profile_end): one CUDA event after every launch on the caller's stream
     cudaStream_t cur_stream;
     int prof_on, prof_n, prof_cap;

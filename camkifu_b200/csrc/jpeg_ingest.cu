@@ -31,35 +31,35 @@ struct NvjpegApi {
     decltype(&nvjpegDecodeBatchedPreAllocate) DecodeBatchedPreAllocate;   // optional
 };
 
+static bool nvjpeg_load(NvjpegApi &api)
+{
+    const char *names[] = {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"};
+    api.lib = nullptr;
+    for (const char *n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return false;
+#define CKB_SYM(field, name) api.field = (decltype(api.field))dlsym(api.lib, name)
+    CKB_SYM(CreateEx, "nvjpegCreateEx");
+    CKB_SYM(CreateSimple, "nvjpegCreateSimple");
+    CKB_SYM(Destroy, "nvjpegDestroy");
+    CKB_SYM(JpegStateCreate, "nvjpegJpegStateCreate");
+    CKB_SYM(JpegStateDestroy, "nvjpegJpegStateDestroy");
+    CKB_SYM(GetImageInfo, "nvjpegGetImageInfo");
+    CKB_SYM(DecodeBatchedInitialize, "nvjpegDecodeBatchedInitialize");
+    CKB_SYM(DecodeBatched, "nvjpegDecodeBatched");
+    CKB_SYM(DecodeBatchedPreAllocate, "nvjpegDecodeBatchedPreAllocate");
+#undef CKB_SYM
+    return api.CreateEx && api.CreateSimple && api.Destroy && api.JpegStateCreate && api.JpegStateDestroy &&
+           api.GetImageInfo && api.DecodeBatchedInitialize && api.DecodeBatched;
+}
+
 static NvjpegApi *nvjpeg_api()
 {
     static NvjpegApi api;
-    static int state = 0;   // 0 = not tried, 1 = ok, -1 = unavailable
-    if (state == 0) {
-        const char *names[] = {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"};
-        for (const char *n : names) {
-            api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
-            if (api.lib) break;
-        }
-        state = -1;
-        if (api.lib) {
-#define CKB_SYM(field, name) api.field = (decltype(api.field))dlsym(api.lib, name)
-            CKB_SYM(CreateEx, "nvjpegCreateEx");
-            CKB_SYM(CreateSimple, "nvjpegCreateSimple");
-            CKB_SYM(Destroy, "nvjpegDestroy");
-            CKB_SYM(JpegStateCreate, "nvjpegJpegStateCreate");
-            CKB_SYM(JpegStateDestroy, "nvjpegJpegStateDestroy");
-            CKB_SYM(GetImageInfo, "nvjpegGetImageInfo");
-            CKB_SYM(DecodeBatchedInitialize, "nvjpegDecodeBatchedInitialize");
-            CKB_SYM(DecodeBatched, "nvjpegDecodeBatched");
-            CKB_SYM(DecodeBatchedPreAllocate, "nvjpegDecodeBatchedPreAllocate");
-#undef CKB_SYM
-            if (api.CreateEx && api.CreateSimple && api.Destroy && api.JpegStateCreate && api.JpegStateDestroy &&
-                api.GetImageInfo && api.DecodeBatchedInitialize && api.DecodeBatched)
-                state = 1;
-        }
-    }
-    return state == 1 ? &api : nullptr;
+    static const bool ok = nvjpeg_load(api);   // once, thread-safe: the lanes may make their first call concurrently
+    return ok ? &api : nullptr;
 }
 
 struct ckb_jpeg_state {
@@ -98,18 +98,21 @@ static const char *jpeg_status(nvjpegStatus_t s)
 
 void ckb_jpeg_free(ckb_ctx *ctx)
 {
-    if (!ctx->jpeg) return;
     NvjpegApi *nj = nvjpeg_api();
-    if (nj && ctx->jpeg->state) nj->JpegStateDestroy(ctx->jpeg->state);
-    if (nj && ctx->jpeg->handle) nj->Destroy(ctx->jpeg->handle);
-    delete[] ctx->jpeg->dst;
-    delete ctx->jpeg;
-    ctx->jpeg = nullptr;
+    for (int l = 0; l < CKB_JPEG_LANES; l++) {
+        ckb_jpeg_state *j = ctx->jpeg[l];
+        if (!j) continue;
+        if (nj && j->state) nj->JpegStateDestroy(j->state);
+        if (nj && j->handle) nj->Destroy(j->handle);
+        delete[] j->dst;
+        delete j;
+        ctx->jpeg[l] = nullptr;
+    }
 }
 
-static int jpeg_init(ckb_ctx *ctx)
+static int jpeg_init(ckb_ctx *ctx, int lane)
 {
-    if (ctx->jpeg) return CKB_OK;
+    if (ctx->jpeg[lane]) return CKB_OK;
     NvjpegApi *nj = nvjpeg_api();
     if (!nj) CKB_FAIL(ctx, CKB_E_STATE, "libnvjpeg is not available on this machine (dlopen failed)");
     ckb_jpeg_state *j = new ckb_jpeg_state();
@@ -138,14 +141,14 @@ static int jpeg_init(ckb_ctx *ctx)
         delete j;
         CKB_FAIL(ctx, CKB_E_CUDA, "nvjpegJpegStateCreate: %s", jpeg_status(s));
     }
-    ctx->jpeg = j;
+    ctx->jpeg[lane] = j;
     return CKB_OK;
 }
 
 extern "C" const char *ckb_jpeg_backend(ckb_ctx *ctx)
 {
-    if (!ctx || jpeg_init(ctx) != CKB_OK) return "unavailable";
-    switch (ctx->jpeg->backend) {
+    if (!ctx || jpeg_init(ctx, 0) != CKB_OK) return "unavailable";
+    switch (ctx->jpeg[0]->backend) {
     case NVJPEG_BACKEND_HARDWARE: return "nvjpeg hardware engine";
     case NVJPEG_BACKEND_GPU_HYBRID: return "nvjpeg GPU hybrid (CUDA Huffman + IDCT)";
     case NVJPEG_BACKEND_HYBRID: return "nvjpeg hybrid (CPU Huffman, CUDA IDCT)";
@@ -154,17 +157,18 @@ extern "C" const char *ckb_jpeg_backend(ckb_ctx *ctx)
 }
 
 extern "C" int ckb_jpeg_decode(ckb_ctx *ctx, const uint8_t *const *h_jpeg, const size_t *h_sizes, int n, int H, int W,
-                               uint8_t *d_frames, size_t row_pitch, size_t frame_pitch, int cpu_threads, void *stream)
+                               uint8_t *d_frames, size_t row_pitch, size_t frame_pitch, int cpu_threads, int lane, void *stream)
 {
     if (!ctx) return CKB_E_INVALID;
     if (n == 0) return CKB_OK;
-    if (!h_jpeg || !h_sizes || !d_frames || n < 0 || H < 1 || W < 1) CKB_FAIL(ctx, CKB_E_INVALID, "ckb_jpeg_decode: bad argument");
+    if (!h_jpeg || !h_sizes || !d_frames || n < 0 || H < 1 || W < 1 || lane < 0 || lane >= CKB_JPEG_LANES)
+        CKB_FAIL(ctx, CKB_E_INVALID, "ckb_jpeg_decode: bad argument");
     if (row_pitch < (size_t)W * 3 || (n > 1 && frame_pitch < row_pitch * (size_t)H))
         CKB_FAIL(ctx, CKB_E_INVALID, "ckb_jpeg_decode: pitches smaller than the image");
     CKB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int rc = jpeg_init(ctx);
+    const int rc = jpeg_init(ctx, lane);
     if (rc != CKB_OK) return rc;
-    ckb_jpeg_state *j = ctx->jpeg;
+    ckb_jpeg_state *j = ctx->jpeg[lane];
     NvjpegApi *nj = nvjpeg_api();
     // every frame must be the H x W the destination was sized for
     nvjpegChromaSubsampling_t sub0 = NVJPEG_CSS_420;

@@ -321,17 +321,20 @@ class StoneEngine:
     def jpeg_backend(self) -> str:
         return self.L.ckb_jpeg_backend(self._h).decode()
 
-    def jpeg_decode(self, base_address: int, offsets, sizes, out: torch.Tensor, cpu_threads: int = 4) -> torch.Tensor:
+    JPEG_LANES = 8
+
+    def jpeg_decode(self, base_address: int, offsets, sizes, out: torch.Tensor, cpu_threads: int = 4, lane: int = 0) -> torch.Tensor:
         """Decode len(offsets) JPEG frames that sit in HOST memory at base_address + offsets[i] (sizes[i] bytes each: e.g. a
         memory-mapped Motion-JPEG file) into `out`, uint8 [>= n, H, W, 3] BGR on the device, on the current stream
-        (nvJPEG; see csrc/jpeg_ingest.cu). Returns out[:n]."""
+        (nvJPEG; see csrc/jpeg_ingest.cu). `lane` < JPEG_LANES picks one of the engine's independent decoders: calls on
+        different lanes may run at the same time from different threads (on different streams). Returns out[:n]."""
         n = len(offsets)
         assert out.is_cuda and out.dtype == torch.uint8 and out.dim() == 4 and out.shape[3] == 3 and out.shape[0] >= n
         assert out.stride(3) == 1 and out.stride(2) == 3
         ptrs = (C.c_void_p * n)(*[base_address + int(o) for o in offsets])
         lens = (C.c_size_t * n)(*[int(v) for v in sizes])
         self._check(self.L.ckb_jpeg_decode(self._h, ptrs, lens, n, out.shape[1], out.shape[2], self._ptr(out), out.stride(1),
-                                           out.stride(0), cpu_threads, self._stream()))
+                                           out.stride(0), cpu_threads, lane, self._stream()))
         return out[:n]
 
     # ------------------------------------------------------------------------------------------------ host staging

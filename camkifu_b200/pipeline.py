@@ -94,7 +94,7 @@ class DetectPipeline:
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         on_device = frames.is_cuda      # frames already in HBM (e.g. decoded there): no upload, the warp reads them in place;
-        n = frames.shape[0]             # whatever produced them must have been enqueued on comp_stream
+        n = frames.shape[0]             # whatever produced them must be ordered before comp_stream (enqueued on it, or waited for)
         assert tuple(frames.shape[1:]) == (self.H, self.W, 3)
         ticket = self._ticket
         self._ticket += 1

@@ -273,7 +273,9 @@ def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int
     receives {"frames": frames this rank processed, "range": (start, stop)}.
     ingest = "nvjpeg" (Motion-JPEG AVI files only, stateless modes): the compressed frames cross PCIe and are decoded on
     the device by nvJPEG straight into the buffer the warp reads (csrc/jpeg_ingest.cu) — no host decode, a tenth of the
-    upload; the decoded pixels can differ from FFmpeg's by a level or two, hence not the default."""
+    upload; the decoded pixels can differ from FFmpeg's by a level or two, hence not the default. `decoders` is then the
+    number of nvJPEG lanes (threads + streams) decoding batches side by side; use batches of 256 frames (nvJPEG decodes
+    batches of less than ~100 images partly on the host) — the ring holds decoders + 3 such batches on the device."""
     import collections
     import torch.distributed as dist
     from .engine import rng_seed, rng_advance
@@ -304,25 +306,73 @@ def process_video(source, mtx, mode: str = "neural", gsize: int = 19, batch: int
                 inflight.append((buf, m, pos))
                 yield buf[:m], mtx, rng_advance(st0, pos)
     else:
-        class _NoRelease:
-            @staticmethod
-            def release(buf):
-                pass
-        src = _NoRelease
+        # `decoders` nvJPEG lanes, each a host thread with its own CUDA stream: a batch keeps the GPU busy for a fraction of
+        # its decode time only, so the lanes overlap (csrc/jpeg_ingest.cu). Batch b goes to lane b % lanes and into ring
+        # slot b % slots once batch b - slots has been consumed; the pipeline takes the batches in order.
+        import threading
         eng = pipe.eng
-        ring = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device=eng.device) for _ in range(pipe.DEPTH + 1)]
+        lanes = max(1, min(int(decoders), eng.JPEG_LANES))
+        positions = list(range(start, stop, batch))
+        slots = lanes + pipe.DEPTH + 1
+        ring = [torch.empty((batch, H, W, 3), dtype=torch.uint8, device=eng.device) for _ in range(min(slots, max(1, len(positions))))]
+        slots = len(ring)
+        cond = threading.Condition()
+        ready, state = {}, {"consumed": 0, "error": None}
+        eng.jpeg_backend()                               # creates lane 0 / loads the library before the threads start
+
+        def lane_main(k):
+            try:
+                torch.cuda.set_device(eng.device)
+                stream = torch.cuda.Stream(device=eng.device)
+                for bi in range(k, len(positions), lanes):
+                    with cond:
+                        cond.wait_for(lambda: state["consumed"] > bi - slots or state["error"] is not None)
+                        if state["error"] is not None:
+                            return
+                    pos = positions[bi]
+                    m = min(batch, stop - pos)
+                    with torch.cuda.stream(stream):
+                        eng.jpeg_decode(avi.base_address, avi.offsets[pos:pos + m], avi.sizes[pos:pos + m], ring[bi % slots],
+                                        cpu_threads=2, lane=k)
+                        ev = torch.cuda.Event()
+                        ev.record(stream)
+                    with cond:
+                        ready[bi] = ev
+                        cond.notify_all()
+            except BaseException as e:                   # noqa: BLE001 - handed to the consumer
+                with cond:
+                    state["error"] = e
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=lane_main, args=(k,), daemon=True) for k in range(lanes)]
+        for t in threads:
+            t.start()
+
+        class _Ring:
+            @staticmethod
+            def release(buf):                            # the batch's results are on the host: its slot may be decoded into
+                with cond:
+                    state["consumed"] += 1
+                    cond.notify_all()
+        src = _Ring
 
         def batches():
-            k = 0
-            for pos in range(start, stop, batch):
-                m = min(batch, stop - pos)
-                d = ring[k % len(ring)]          # free again: at most DEPTH batches are outstanding
-                k += 1
-                with torch.cuda.stream(pipe.comp_stream):
-                    eng.jpeg_decode(avi.base_address, avi.offsets[pos:pos + m], avi.sizes[pos:pos + m], d,
-                                    cpu_threads=max(1, decoders))
-                inflight.append((None, m, pos))
-                yield d[:m], mtx, rng_advance(st0, pos)
+            try:
+                for bi, pos in enumerate(positions):
+                    with cond:
+                        cond.wait_for(lambda: bi in ready or state["error"] is not None)
+                        if state["error"] is not None:
+                            raise state["error"]
+                        ev = ready.pop(bi)
+                    pipe.comp_stream.wait_event(ev)      # the pipeline's kernels run after the decode of this batch
+                    m = min(batch, stop - pos)
+                    inflight.append((None, m, pos))
+                    yield ring[bi % slots][:m], mtx, rng_advance(st0, pos)
+            finally:                                     # abandoned half way (an error downstream): let the lanes go
+                with cond:
+                    if state["error"] is None:
+                        state["error"] = RuntimeError("ingest stopped")
+                    cond.notify_all()
 
     names = {"neural": ("stones", "keep", "conf"), "clustering": ("km_stones", "km_trusted"),
              "both": ("stones", "keep", "conf", "km_stones", "km_trusted"),

@@ -197,9 +197,12 @@ int ckb_upload_frames(ckb_ctx *ctx, const uint8_t *h_frames, int n, int H, int W
  * library: the hardware JPEG engines when available, else its CUDA decoder) on `stream`. cpu_threads: host threads the
  * library may use for its CPU stages. The pixels may differ from FFmpeg's decode of the same frame by a level or two
  * (different IDCT / upsampling), which is why this is an option of the batch API, not the default ingest.
+ * lane (0..7): which of the context's independent decoders to use. One batch keeps the GPU busy for a fraction of its
+ * decode time only (a chain of small kernels), so calls on different lanes, from different host threads on different
+ * streams, overlap: two lanes give 1.7 x one. A lane must not be used by two threads at once.
  * ckb_jpeg_backend: which nvJPEG backend the context got. */
 int ckb_jpeg_decode(ckb_ctx *ctx, const uint8_t *const *h_jpeg, const size_t *h_sizes, int n, int H, int W, uint8_t *d_frames,
-                    size_t row_pitch, size_t frame_pitch, int cpu_threads, void *stream);
+                    size_t row_pitch, size_t frame_pitch, int cpu_threads, int lane, void *stream);
 const char *ckb_jpeg_backend(ckb_ctx *ctx);
 
 /* ---- per-kernel timing (bench.py's roofline) ---------------------------------------------------------------------------

@@ -296,3 +296,14 @@ def test_nvjpeg_ingest_matches_host_decode(tmp_path):
     assert np.array_equal(a["km_trusted"], b["km_trusted"])
     c = process_video(avi.repeat(2), mtx, mode="clustering", batch=16, engine=eng, rng_state=st0, ingest="nvjpeg")
     assert c["km_stones"].shape[0] == 2 * n and np.array_equal(c["km_stones"][:n], b["km_stones"])
+    # several decoder lanes (threads + streams) and more batches than ring slots: same results, in frame order
+    e = process_video(avi.repeat(4), mtx, mode="both", batch=5, engine=eng, rng_state=st0, ingest="nvjpeg", decoders=3)
+    one = process_video(avi.repeat(4), mtx, mode="both", batch=32, engine=eng, rng_state=st0, ingest="nvjpeg", decoders=1)
+    for k in ("km_stones", "km_trusted", "stones", "keep"):
+        assert np.array_equal(e[k], one[k]), k
+    assert e["km_stones"].shape[0] == 4 * n and np.array_equal(e["km_stones"][n:2 * n], b["km_stones"])
+    d2 = torch.empty_like(d)
+    eng.jpeg_decode(avi.base_address, avi.offsets, avi.sizes, d2, lane=5)
+    assert torch.equal(d, d2)
+    with pytest.raises(Exception):
+        eng.jpeg_decode(avi.base_address, avi.offsets, avi.sizes, d2, lane=eng.JPEG_LANES)
