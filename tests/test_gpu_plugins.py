@@ -297,6 +297,7 @@ def test_nvjpeg_ingest_matches_host_decode(tmp_path):
     c = process_video(avi.repeat(2), mtx, mode="clustering", batch=16, engine=eng, rng_state=st0, ingest="nvjpeg")
     assert c["km_stones"].shape[0] == 2 * n and np.array_equal(c["km_stones"][:n], b["km_stones"])
     # several decoder lanes (threads + streams) and more batches than ring slots: same results, in frame order
+    eng.set_cnn_weights(weights.glorot_params(seed=0))
     e = process_video(avi.repeat(4), mtx, mode="both", batch=5, engine=eng, rng_state=st0, ingest="nvjpeg", decoders=3)
     one = process_video(avi.repeat(4), mtx, mode="both", batch=32, engine=eng, rng_state=st0, ingest="nvjpeg", decoders=1)
     for k in ("km_stones", "km_trusted", "stones", "keep"):
