@@ -101,6 +101,29 @@ def test_tc_matches_simt_on_noise(engine):
     assert err.max() <= SOFTMAX_RTOL, "softmax error %.3g" % err.max()
 
 
+@pytest.mark.parametrize("n", [5, 17, 64])
+def test_tc_pool_fused_over_tile_ranges(engine, n):
+    """conv4's epilogue pools across tile boundaries (every CTA takes a contiguous range of 128-pixel tiles and recomputes
+    the tile in front of it): batch sizes that split the tiles over the CTAs differently — fewer tiles than CTAs + 1, an
+    uneven split, the full 64-frame pass — against the fp32 CUDA-core path, every patch."""
+    rng = np.random.default_rng(100 + n)
+    base = boards(2, seed=9)
+    goban = np.empty((n, 380, 380, 3), np.uint8)
+    for k in range(n):
+        noise = rng.integers(-40, 41, (380, 380, 3))
+        goban[k] = np.clip(np.roll(base[k % 2], (7 * k) % 380, axis=(k % 2)).astype(np.int64) + noise, 0, 255)
+    g = torch.from_numpy(goban).cuda()
+    a = engine.cnn_forward(g)
+    b = engine.cnn_forward(g, simt=True)
+    ya, yb = a["softmax"].cpu().numpy(), b["softmax"].cpu().numpy()
+    err = np.abs(ya - yb).max(axis=2) / yb.max(axis=2)
+    assert err.max() <= SOFTMAX_RTOL, "softmax error %.3g" % err.max()
+    top2 = np.sort(yb, axis=2)[:, :, -2:]
+    clear = (top2[:, :, 1] - top2[:, :, 0]) > 2e-3 * top2[:, :, 1]      # ties within the tolerance may flip
+    assert np.array_equal(ya.argmax(2)[clear], yb.argmax(2)[clear])
+    assert clear.mean() > 0.99
+
+
 def test_tc_forward_trained_weights(oracle, golden):
     """Realistic weights (tests/golden/sfneural_trained.npz: the reference architecture trained on synthetic boards by
     oracle/train_fixture.py — the reference's own model does not ship): peaked softmax outputs, large logits. Same bar:
