@@ -480,6 +480,20 @@ __global__ void cnn_tc_unpack(const uint4 *__restrict__ in, long long in_plane, 
         if (c * 8 + k < C) out[p * C + c * 8 + k] = v[k];
 }
 
+// test aid: fc1's per-tap planes (the pooled conv4 output: plane (pl * 36 + q) * 12 + chunk, row = patch) -> dense float32
+// [patch][q = y * 6 + x][90]
+__global__ void cnn_tc_unpack_taps(const uint4 *__restrict__ in, long long in_plane, int n_patches, float *__restrict__ out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_patches * 36 * 12) return;
+    const int patch = (int)(idx % n_patches);
+    const int qc = (int)(idx / n_patches), q = qc / 12, c = qc - 12 * q;
+    float v[8];
+    unpack8(in[(long long)(q * 12 + c) * in_plane + patch], in[(long long)((36 + q) * 12 + c) * in_plane + patch], v);
+    for (int k = 0; k < 8; k++)
+        if (c * 8 + k < 90) out[((size_t)patch * 36 + q) * 90 + c * 8 + k] = v[k];
+}
+
 // ------------------------------------------------------------------------------------------------ host: weight packing
 static inline uint16_t bf16_rn(float f)
 {
@@ -715,7 +729,7 @@ extern "C" int ckb_cnn_set_debug(ckb_ctx *ctx, int on)
 
 // Test aid: after ckb_cnn_forward on n <= 64 frames, unpack one intermediate activation of the tensor-core path from
 // the workspace into dense float32 [patch][H][W][C]: layer 1 = conv1 (36,36,32), 2 = pooled conv2 (16,16,32),
-// 3 = conv3 (14,14,90), 4 = pooled conv4 (6,6,90; from fc1's tap planes), 5 = fc1 (160).
+// 3 = conv3 (14,14,90), 4 = pooled conv4 (6,6,90; from fc1's tap planes, written by conv4's epilogue), 5 = fc1 (160).
 extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n, int layer, float *d_out, void *stream)
 {
     if (!ctx || !d_work || !d_out || n < 1 || n > TC_MAX_FRAMES) return CKB_E_INVALID;
@@ -735,8 +749,11 @@ extern "C" int ckb_cnn_debug_activation(ckb_ctx *ctx, const void *d_work, int n,
         break;
     case 2: go(W.p2, W.p2_plane, 4, P * 256, 32); break;
     case 3: go(W.a3, W.a3_plane, 12, P * 196, 90); break;
+    case 4:
+        cnn_tc_unpack_taps<<<(unsigned)((P * 36 * 12 + 255) / 256), 256, 0, st>>>((const uint4 *)(work + W.p4), W.p4_plane, (int)P, d_out);
+        break;
     case 5: CKB_CUDA(ctx, cudaMemcpyAsync(d_out, work + W.f5, (size_t)P * 160 * 4, cudaMemcpyDeviceToDevice, st)); return CKB_OK;
-    default: CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_debug_activation: layer must be 1, 2, 3 or 5");
+    default: CKB_FAIL(ctx, CKB_E_INVALID, "ckb_cnn_debug_activation: layer must be 1 .. 5");
     }
     CKB_LAUNCH_CHECK(ctx, "cnn_tc_unpack");
     return CKB_OK;

@@ -311,7 +311,7 @@ class StoneEngine:
 
     def cnn_debug_activation(self, n: int, layer: int) -> torch.Tensor:
         """Test aid: dense float32 copy of an intermediate activation of the last cnn_forward (n <= 64 frames)."""
-        shape = {1: (36, 36, 32), 2: (16, 16, 32), 3: (14, 14, 90), 5: (160,)}[layer]
+        shape = {1: (36, 36, 32), 2: (16, 16, 32), 3: (14, 14, 90), 4: (6, 6, 90), 5: (160,)}[layer]
         out = torch.zeros((n * 100,) + shape, dtype=torch.float32, device=self.device)
         self._check(self.L.ckb_cnn_debug_activation(self._h, self._ptr(self._work["cnn"]), n, layer, self._ptr(out),
                                                     self._stream()))

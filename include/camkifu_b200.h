@@ -170,7 +170,7 @@ int ckb_cnn_forward(ckb_ctx *ctx, const uint8_t *d_goban, int n, void *d_work, s
  * same arguments, but d_work must hold ckb_cnn_workspace_simt(ctx, n) bytes. ckb_cnn_debug_activation: after
  * ckb_cnn_forward on n <= 64 frames, unpacks one intermediate activation of the tensor-core path from its workspace into
  * dense float32 [patch][H][W][C]: layer 1 = conv1 (36,36,32), 2 = pooled conv2 (16,16,32), 3 = conv3 (14,14,90),
- * 5 = fc1 (160). conv1's activations normally never leave shared memory (gather + conv1 + conv2 + pool are one kernel):
+ * 4 = pooled conv4 (6,6,90), 5 = fc1 (160). conv1's activations normally never leave shared memory (gather + conv1 + conv2 + pool are one kernel):
  * ckb_cnn_set_debug(ctx, 1) makes the following forward passes also write them to the workspace (which grows:
  * query ckb_cnn_workspace again) so that layer 1 can be inspected. */
 int ckb_cnn_set_debug(ckb_ctx *ctx, int on);
