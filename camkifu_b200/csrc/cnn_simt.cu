@@ -181,36 +181,60 @@ int ckb_launch_decode(ckb_ctx *ctx, const float *d_logits, int n, float *d_softm
 #define FC2_R 4
 #define FC2_WFLOATS ((CNN_F5 * CNN_F6 + CNN_F6 + 3) / 4 * 4)
 #define FC2_SMEM ((FC2_WFLOATS + (FC2_THREADS / 32) * FC2_R * CNN_F5) * 4)
-static_assert((OFF_W6 % 4) == 0 && (CNN_F5 * CNN_F6) % 4 == 0 && CNN_F5 % 4 == 0, "16-byte loads of fc2's weights / inputs");
-__global__ void __launch_bounds__(FC2_THREADS) cnn_fc2_softmax_label(const float *__restrict__ f5, const float *__restrict__ w,
+static_assert((OFF_W6 % 4) == 0 && (CNN_F5 * CNN_F6) % 4 == 0 && CNN_F5 % 4 == 0 && CNN_F6 <= FC2_THREADS, "16-byte loads of fc2's weights / inputs");
+__global__ void __launch_bounds__(FC2_THREADS, 2) cnn_fc2_softmax_label(const float *__restrict__ f5, const float *__restrict__ w,
                                                                      const float *__restrict__ b, int n_regions,
                                                                      float *__restrict__ softmax, int *__restrict__ label,
                                                                      float *__restrict__ conf)
 {
     extern __shared__ __align__(16) float s_w[];         // [160][81] weights, [81] biases, then [warp][FC2_R][160] inputs
-    {
-        const float4 *w4 = (const float4 *)w;
-        float4 *s4 = (float4 *)s_w;
-#pragma unroll 13
-        for (int i = threadIdx.x; i < CNN_F5 * CNN_F6 / 4; i += FC2_THREADS) s4[i] = __ldg(w4 + i);
-        for (int i = threadIdx.x; i < CNN_F6; i += FC2_THREADS) s_w[CNN_F5 * CNN_F6 + i] = __ldg(b + i);
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool has2 = lane + 64 < CNN_F6;
     float *s_x = s_w + FC2_WFLOATS + wib * (FC2_R * CNN_F5);
     const int n_groups = (n_regions + FC2_R - 1) / FC2_R;
-    for (int grp = blockIdx.x * (FC2_THREADS / 32) + wib; grp < n_groups; grp += gridDim.x * (FC2_THREADS / 32)) {
+    constexpr int XV = FC2_R * CNN_F5 / 4 / 32;          // 16-byte units of a group's inputs per lane
+    static_assert(FC2_R * CNN_F5 / 4 % 32 == 0, "a group's inputs split evenly over the lanes");
+    // a group's inputs: FC2_R x 160 consecutive floats of f5
+    auto load_x = [&](int grp, float4 *xr) {
+        const int reg0 = grp * FC2_R, nr = min(FC2_R, n_regions - reg0);
+        const float4 *x4 = (const float4 *)(f5 + (size_t)reg0 * CNN_F5);
+#pragma unroll
+        for (int u = 0; u < XV; u++) {
+            const int i = lane + 32 * u;
+            xr[u] = (grp < n_groups && i < nr * (CNN_F5 / 4)) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    const int grp0 = blockIdx.x * (FC2_THREADS / 32) + wib;
+    float4 xr[XV];
+    load_x(grp0, xr);                                    // in flight together with the weights
+    {
+        // all of a thread's loads are issued before the first store: a fixed trip count with predicates, not a loop whose
+        // remainder runs one L2 round trip per iteration
+        constexpr int NW4 = CNN_F5 * CNN_F6 / 4, PER = (NW4 + FC2_THREADS - 1) / FC2_THREADS;
+        const float4 *w4 = (const float4 *)w;
+        float4 *s4 = (float4 *)s_w;
+        float4 wv[PER];
+#pragma unroll
+        for (int it = 0; it < PER; it++) {
+            const int i = threadIdx.x + it * FC2_THREADS;
+            wv[it] = i < NW4 ? __ldg(w4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float bv = threadIdx.x < CNN_F6 ? __ldg(b + threadIdx.x) : 0.f;
+#pragma unroll
+        for (int it = 0; it < PER; it++) {
+            const int i = threadIdx.x + it * FC2_THREADS;
+            if (i < NW4) s4[i] = wv[it];
+        }
+        if (threadIdx.x < CNN_F6) s_w[CNN_F5 * CNN_F6 + threadIdx.x] = bv;
+    }
+    __syncthreads();
+    for (int grp = grp0; grp < n_groups; grp += gridDim.x * (FC2_THREADS / 32)) {
         const int reg0 = grp * FC2_R;
         const int nr = min(FC2_R, n_regions - reg0);
+        if (grp != grp0) load_x(grp, xr);
         __syncwarp();                                    // the previous group's walk has finished with s_x
-        {   // the group's inputs: FC2_R x 160 consecutive floats of f5
-            const float4 *x4 = (const float4 *)(f5 + (size_t)reg0 * CNN_F5);
-            float4 *d4 = (float4 *)s_x;
 #pragma unroll
-            for (int i = lane; i < FC2_R * CNN_F5 / 4; i += 32)
-                d4[i] = i < nr * (CNN_F5 / 4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int u = 0; u < XV; u++) ((float4 *)s_x)[lane + 32 * u] = xr[u];
         __syncwarp();
         float a0[FC2_R], a1[FC2_R], a2[FC2_R];
 #pragma unroll
