@@ -124,3 +124,17 @@ def test_mjpeg_avi_index(tmp_path):
     other.write_bytes(b"\x00" * 64)
     with pytest.raises(ValueError):
         MjpegAvi(str(other))
+
+
+def test_nvjpeg_ingest_argument_checks(tmp_path):
+    """ingest="nvjpeg" is for Motion-JPEG AVI files and stateless modes: anything else is refused before any device work."""
+    from camkifu_b200.video import process_video
+    frames = np.zeros((4, 24, 32, 3), np.uint8)
+    with pytest.raises(ValueError):
+        process_video(frames, np.eye(3), mode="neural", ingest="nvjpeg")
+    other = tmp_path / "clip.bin"
+    other.write_bytes(b"RIFF" + b"\x00" * 60)
+    with pytest.raises(ValueError):
+        process_video(str(other), np.eye(3), mode="neural", ingest="nvjpeg")
+    with pytest.raises(ValueError):
+        process_video(str(other), np.eye(3), mode="full", ingest="nvjpeg")
