@@ -53,7 +53,7 @@ KMEANS_BYTES_PER_FRAME = 3 * N_FULL + 4 * N_FULL + 1083          # SURVEY.md 8(d
 # (None = no capture of the current kernel yet)
 DRAM_TRAFFIC = {
     "cnn_tc_front": 28010400 + 151286000,         # profiles/r1q_kernels_ncu_full_selected.csv
-    "ckb_warp_kernel": 2 * (94518016 + 7100000),  # two 32-frame launches per step; profiles/r2_warp_ncu_full_selected.csv
+    "ckb_warp_kernel": 2 * (94518016 + 7100000),  # per 64 frames (captured as two 32-frame launches); profiles/r2_warp_ncu_full_selected.csv
     # cluster kernel 27.75 MB (the 64 images, read once, nothing written) + zone vote 28.63 MB (reads them again);
     # profiles/r2_stats_kernels_ncu_full_selected.csv
     "ckb_kmeans_cluster": 27749376 + 28633088,

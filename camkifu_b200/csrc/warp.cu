@@ -281,8 +281,10 @@ int ckb_launch_warp(ckb_ctx *ctx, const uint8_t *d_frames, int n, int H, int W, 
     const int S = ctx->S;
     const int threads = 128;
     const int work = (S >> 2) * S;
-    for (int f0 = 0; f0 < n; f0 += CKB_WARP_CHUNK) {
-        const int nf = n - f0 < CKB_WARP_CHUNK ? n - f0 : CKB_WARP_CHUNK;
+    // one homography for the whole batch (a video segment): a single launch; per-frame matrices travel 32 at a time
+    const int chunk = n_mtx == 1 ? 65535 : CKB_WARP_CHUNK;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int nf = n - f0 < chunk ? n - f0 : chunk;
         WarpMats mats;
         if (n_mtx == 1)
             memcpy(mats.m[0], h_minv, 9 * sizeof(double));
