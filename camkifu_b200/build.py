@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
             print(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-    subprocess.run([nvcc(), "-shared", "-o", out] + objs + ["-lcudart", "-ldl"], check=True)
+    # the arch on the link line too: nvcc otherwise adds a device-link stub for its default architecture (sm_52)
+    subprocess.run([nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart", "-ldl"], check=True)
     return out
 
 
